@@ -1,0 +1,272 @@
+/* r3d_gpu.h -- C ABI of the B200-native phonon-propagate path of Radiative3D.
+ *
+ * This is the drop-in boundary for ONE path of the reference program: the body
+ * of the per-phonon loop in Model::RunSimulation (reference model.cpp:611-625),
+ * i.e. ShearDislocation::GenerateEventPhonon (events.cpp:111-124) followed by
+ * Phonon::Propagate (phonons.cpp:540-682) with everything it reaches
+ * (media.cpp, media_cellface.cpp, raypath.cpp, rtcoef.cpp, scatterers.cpp:297-363,
+ * probability.cpp:104-129, dataout.cpp:103-216,545-617).
+ *
+ * The reference has no FFI for this path (the loop is hard-wired and talks to
+ * global singletons), so the boundary is defined here: the host program builds
+ * its model exactly as before, FLATTENS it into the plain arrays of
+ * r3d_model_desc, and calls r3d_create / r3d_run / r3d_fetch in place of the
+ * loop; r3d_fetch returns the seismometer bins and loss counters which the host
+ * writes back into its Seismometer / DataReporter objects before calling its
+ * unchanged file writers (dataout.cpp:249-406,623-694).  INTEGRATION.md shows
+ * the reference-side stub.
+ *
+ * Conventions: plain pointers and sizes, no C++ types, no exceptions cross the
+ * ABI.  Every function returning int returns 0 on success and a non-zero
+ * R3D_E* code otherwise; r3d_last_error() then holds a message (thread-local).
+ * All descriptor arrays are BORROWED for the duration of r3d_create only.
+ * There is no CPU fallback: with no usable CUDA device r3d_create fails.
+ */
+#ifndef R3D_GPU_H_
+#define R3D_GPU_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R3D_ABI_VERSION 1
+
+/* error codes */
+#define R3D_OK            0
+#define R3D_EINVAL        1   /* bad descriptor / argument               */
+#define R3D_ECUDA         2   /* CUDA runtime error (message has detail) */
+#define R3D_ENODEV        3   /* no usable CUDA device                   */
+#define R3D_ENOMEM        4
+#define R3D_EUNSUPPORTED  5
+
+/* ray types (reference raytype.hpp:12-20) */
+#define R3D_RAY_P   0
+#define R3D_RAY_S   1
+#define R3D_RAY_SH  1
+#define R3D_RAY_SV  2
+
+/* cell kinds: one kind per model, as in the reference (model.cpp:378-411) */
+#define R3D_CELL_CYLINDER 0   /* RCUCylinder, media.hpp:309  */
+#define R3D_CELL_TETRA    1   /* Tetra,       media.hpp:397  */
+#define R3D_CELL_SHELL    2   /* SphereShell, media.hpp:462  */
+
+/* face flag bits (CellFace::mCollect/mReflect/mAdjoin/mGridDiscon,
+ * media_cellface.hpp:120-126) */
+#define R3D_FACE_COLLECT 1u
+#define R3D_FACE_REFLECT 2u
+#define R3D_FACE_ADJOIN  4u
+#define R3D_FACE_DISCON  8u
+
+/* faces per cell and face ids (media_cellface.hpp:96-107) */
+#define R3D_CYL_NFACES    3   /* TOP=0, BOTTOM=1, SIDE=2 (shared loss face) */
+#define R3D_SHELL_NFACES  2   /* TOP=0, BOTTOM=1 */
+#define R3D_TETRA_NFACES  4   /* A..D = 0..3 */
+
+/* per-cell parameter records, in doubles.
+ *
+ * CYLINDER (media.cpp:135-158): only the TOP velocities/Q/density are used.
+ *   [0..1] vel P,S   [2] density   [3..4] Q P,S
+ *   [5..7] top normal  [8..10] top point  [11..13] bottom normal  [14..16] bottom point
+ * SHELL (media.cpp:578-626):  v(r) = C + A r^2
+ *   [0..1] A P,S  [2..3] C P,S  [4..5] zeroRadius^2 P,S  [6] densA  [7] densC
+ *   [8..9] Q P,S  [10] signed radius top (+R)  [11] signed radius bottom (-R, -0.0 at centre)
+ *   [12] Rtop^2  [13] Rbot^2
+ * TETRA (media.cpp:353-395):  v(x) = g.x + v0
+ *   [0..2] grad P  [3..5] grad S  [6..7] v0 P,S  [8..10] density grad  [11] density0
+ *   [12..13] Q P,S  [14+6f .. 14+6f+2] face f normal  [14+6f+3 .. +5] face f point
+ */
+#define R3D_CYL_NPARAM   17
+#define R3D_SHELL_NPARAM 14
+#define R3D_TETRA_NPARAM 38
+
+/* seismometer record, in doubles (dataout.cpp:42-71):
+ *   [0..2] loc  [3..5] X1  [6..8] X2  [9..11] X3
+ *   [12..13] inner radius P,S  [14..15] outer radius P,S  [16..17] area P,S */
+#define R3D_SEIS_NPARAM 18
+
+/* bin record layout returned by r3d_fetch (dataout.hpp:77-93):
+ *   energies[s][b][0..2] = X1,X2,X3 axis energy, [3..4] = energy by type P,S
+ *   counts  [s][b][0..1] = phonon count by type P,S (u64 here; u32 in reference) */
+#define R3D_BIN_NF64 5
+#define R3D_BIN_NCNT 2
+
+/* counters returned by r3d_fetch (dataout.cpp:591-617) */
+#define R3D_CNT_LOST     0
+#define R3D_CNT_TIMEOUT  1
+#define R3D_CNT_INVALID  2
+#define R3D_CNT_EVENTS   3   /* propagate-loop iterations (phonons.cpp:542), extension */
+#define R3D_CNT_CATCHES  4   /* bin updates (dataout.cpp:200-212), extension            */
+#define R3D_CNT_SCATTERS 5   /* scatter events (phonons.cpp:605-618), extension         */
+#define R3D_NCOUNTERS    8
+
+/* invalid-phonon reasons, bit index into diag (dataout.hpp:229-237) */
+#define R3D_INV_PATH_NAN      0
+#define R3D_INV_TIME_NAN      1
+#define R3D_INV_PATH_NEGATIVE 2
+#define R3D_INV_TIME_NEGATIVE 3
+#define R3D_INV_STUCK         4
+#define R3D_INV_SLOW          5
+#define R3D_INV_LOOP_EXCEED   6
+
+/* fates in r3d_phonon_final */
+#define R3D_FATE_LOST    1
+#define R3D_FATE_TIMEOUT 2
+#define R3D_FATE_INVALID 3
+
+typedef struct r3d_model_desc {
+  /* ---- globals (class statics set by the Model ctor, model.cpp:271-299) ---- */
+  double   freq_hz;        /* MediumCell::cmPhononFreq                           */
+  double   ttl;            /* Phonon::cm_ttl                                     */
+  double   bin_dt;         /* Seismometer::cmTimePerBin                          */
+  uint32_t n_bins;         /* Seismometer::cmNumBins                             */
+  int32_t  ecs_radial;     /* 0: up=(0,0,1) (ENU/RAE ortho); 1: up radial from   */
+  double   earth_center[3];/*    earth_center (RAE curved/spherical, ecs.cpp:147)*/
+  double   min_theta;      /* Phonon::cm_min_theta (1e-7)                        */
+  double   max_theta;      /* Phonon::cm_max_theta (pi-1e-7)                     */
+  double   slow_concern;   /* Phonon::cm_slow_concern (0.001)                    */
+  uint64_t loop_concern;   /* Phonon::cm_loop_concern (2^20)                     */
+  int32_t  no_deflect;     /* Scatterer::cm_NoDeflect_b                          */
+  int32_t  reserved0;
+  /* ---- take-off-angle set (PhononSource::pTOA) ---- */
+  uint32_t n_toa;
+  uint32_t reserved1;
+  const double *toa_theta; /* [n_toa] */
+  const double *toa_phi;   /* [n_toa] */
+  /* ---- event source (ShearDislocation, events.cpp:42-107) ---- */
+  double   src_loc[3];
+  uint32_t src_cell;
+  uint32_t reserved2;
+  const double *src_whole_cdf; /* [3]        cumulative, P,SH,SV (mWholeProbs[0]) */
+  const double *src_cdf;       /* [3][n_toa] cumulative (mPDists[P|SH|SV])        */
+  /* ---- scatterers (scatterers.cpp:97-220) ---- */
+  uint32_t n_scat;
+  uint32_t reserved3;
+  const double *scat_mfp;       /* [n_scat][2]        mean free path P,S            */
+  const double *scat_whole_cdf; /* [n_scat][2][4]     cumulative (mWholeProbs[in])  */
+  const double *scat_cdf;       /* [n_scat][4][n_toa] cumulative PP,PS,SP,SS        */
+  const double *scat_spol;      /* [n_scat][n_toa]    S->S polarisation angle       */
+  /* ---- cells ---- */
+  uint32_t n_cells;
+  uint32_t cell_kind;      /* R3D_CELL_*                                  */
+  uint32_t cell_nparam;    /* R3D_*_NPARAM matching cell_kind             */
+  uint32_t faces_per_cell; /* R3D_*_NFACES matching cell_kind             */
+  const double   *cell_params;     /* [n_cells][cell_nparam]              */
+  const uint32_t *cell_scat;       /* [n_cells] scatterer index           */
+  const uint8_t  *face_flags;      /* [n_cells][faces_per_cell]           */
+  const uint32_t *face_other_cell; /* [n_cells][faces_per_cell]; ignored  */
+                                   /*   unless R3D_FACE_ADJOIN is set     */
+  double   cyl_radius2;    /* RCUCylinder::cmLossFace.mRad2 (cylinder only)*/
+  /* ---- seismometers (dataout.cpp:42-71) ---- */
+  uint32_t n_seis;
+  uint32_t reserved4;
+  const double *seis;      /* [n_seis][R3D_SEIS_NPARAM] */
+} r3d_model_desc;
+
+/* per-phonon end state, for parity tests (r3d_trace) */
+typedef struct r3d_phonon_final {
+  double   time, pathlen, amp;
+  double   loc[3];
+  double   theta, phi, pol;
+  uint32_t moves;      /* Phonon::mMoveCount                          */
+  uint32_t cell;       /* index of the cell the phonon died in        */
+  uint32_t type;       /* R3D_RAY_P / R3D_RAY_S                       */
+  uint32_t fate;       /* R3D_FATE_* ; for INVALID, reason in bits 8+ */
+  uint32_t draws;      /* RNG draws consumed                          */
+  uint32_t catches;    /* bin updates made                            */
+  uint32_t scatters;   /* scatter events                              */
+  uint32_t iters;      /* loop iterations                             */
+} r3d_phonon_final;
+
+typedef struct r3d_handle r3d_handle;
+
+/* Upload a model to `n_dev` CUDA devices (replicated) and allocate
+ * zeroed bins.  devices==NULL means device 0..n_dev-1. */
+int r3d_create(const r3d_model_desc *desc, const int *devices, int n_dev,
+               r3d_handle **out);
+
+/* Trace phonons [first_phonon, first_phonon+n_phonons) and ACCUMULATE into the
+ * bins / counters.  Phonon i always uses the Philox4x32-10 stream keyed by
+ * (seed, i), so the result does not depend on how a range is split across
+ * calls, devices or ranks (up to floating-point summation order).  The index
+ * range is sharded contiguously across the handle's devices.  Asynchronous:
+ * returns after enqueueing; r3d_sync / r3d_fetch wait. */
+int r3d_run(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons, uint64_t seed);
+
+/* Wait for all enqueued work.  If device_seconds!=NULL it receives the device
+ * time (CUDA events, max over devices) of the r3d_run calls since the last
+ * r3d_sync. */
+int r3d_sync(r3d_handle *h, double *device_seconds);
+
+/* Synchronise, sum over the handle's devices, copy out.  Any pointer may be
+ * NULL.  energies: [n_seis][n_bins][5] f64; counts: [n_seis][n_bins][2] u64;
+ * counters: [R3D_NCOUNTERS]; diag: OR of (1<<R3D_INV_*). */
+int r3d_fetch(r3d_handle *h, double *energies, uint64_t *counts,
+              uint64_t *counters, uint32_t *diag);
+
+/* Zero bins and counters on all devices. */
+int r3d_reset(r3d_handle *h);
+
+/* Device pointers of device `dev_slot`'s accumulators, so a multi-process
+ * launcher can all-reduce them in place (e.g. torch.distributed/NCCL on a
+ * tensor wrapping the memory): energies f64[n_seis*n_bins*5], counts
+ * u64[n_seis*n_bins*2], counters u64[R3D_NCOUNTERS] (diag is counters[7]). */
+int r3d_device_accumulators(r3d_handle *h, int dev_slot, void **energies,
+                            void **counts, void **counters);
+
+/* The CUDA stream r3d_run launches on for `dev_slot` (a cudaStream_t). */
+int r3d_stream(r3d_handle *h, int dev_slot, void **stream);
+
+/* Number of kernels this handle has launched so far. */
+int r3d_launch_count(r3d_handle *h, uint64_t *n);
+
+/* Parity hook: trace phonons [first, first+n) on device slot 0 WITHOUT touching
+ * the accumulators' semantics (bins are still accumulated) and write each
+ * phonon's end state to out[n] (host memory). */
+int r3d_trace(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons,
+              uint64_t seed, r3d_phonon_final *out);
+
+/* ---- deterministic sub-kernel hooks (parity at 1e-10) ----------
+ * Each evaluates n independent cases on the device with the same device
+ * functions the propagate kernel uses. */
+
+/* ProbDist::GetRandomIndex (probability.cpp:104-129) on cdf[n_cdf] for the
+ * 31-bit draws k[n]: out[i] = smallest j with cdf[n_cdf-1]*(k/RAND_MAX) <= cdf[j]. */
+int r3d_test_cdf_search(const double *cdf, uint32_t n_cdf, const uint32_t *k,
+                        uint32_t n, uint32_t *out, int use_guide_table);
+
+/* GetPathToBoundary (media.cpp:236,518,668) for phonons in given cells:
+ * in[i] = {cell, type, x,y,z, theta, phi} as 7 doubles;
+ * out[i] = {pathlen, time, x,y,z, theta, phi, atten, face} as 9 doubles. */
+int r3d_test_path_to_boundary(r3d_handle *h, const double *in, uint32_t n, double *out);
+
+/* AdvanceLength (media.cpp:208,442,859): in[i] = {cell,type,x,y,z,theta,phi,len};
+ * out as above with face = -1. */
+int r3d_test_advance(r3d_handle *h, const double *in, uint32_t n, double *out);
+
+/* Phonon::Transform (phonons.cpp:116-170): in[i] = {theta,phi,pol, rtheta,rphi,rpol};
+ * out[i] = {theta,phi,pol}. */
+int r3d_test_transform(const double *in, uint32_t n, double *out);
+
+/* RTCoef (rtcoef.cpp:30-588): in[i] = {nx,ny,nz, dx,dy,dz, rhoR, vpR, vsR, rhoT, vpT, vsT,
+ * intype(0 P,1 SH,2 SV), notransmit, k_choose}; out[i] = {prob[6] (R_P,R_SV,R_SH,T_P,T_SV,T_SH),
+ * choice, dirx,diry,dirz, pdx,pdy,pdz}. */
+int r3d_test_rtcoef(const double *in, uint32_t n, double *out);
+
+/* Seismometer::CatchPhonon (dataout.cpp:103-216) for one seismometer record:
+ * in[i] = {seis[18], time, x,y,z, theta,phi,pol, type, amp, vel};
+ * out[i] = {caught(0/1), bin, ex,ey,ez, e}. */
+int r3d_test_catch(double bin_dt, uint32_t n_bins, const double *in, uint32_t n, double *out);
+
+void r3d_destroy(r3d_handle *h);
+
+const char *r3d_last_error(void);
+
+int r3d_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R3D_GPU_H_ */
