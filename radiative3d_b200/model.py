@@ -160,15 +160,3 @@ class FlatModel:
                 f.write(struct.pack("<Q", a.nbytes))
                 f.write(a.tobytes())
                 f.write(b"\0" * ((8 - a.nbytes % 8) % 8))
-
-
-def load_bins(path):
-    """Read an "R3DBINS1" result file (written by oracle/ref_harness.cpp and by save_bins)."""
-    with open(path, "rb") as f:
-        if f.read(8) != b"R3DBINS1":
-            raise ValueError(f"{path}: not an R3DBINS1 file")
-        ns, nb = struct.unpack("<II", f.read(8))
-        counters = np.fromfile(f, dtype="<u8", count=abi.R3D_NCOUNTERS)
-        energies = np.fromfile(f, dtype="<f8", count=ns * nb * 5).reshape(ns, nb, 5)
-        counts = np.fromfile(f, dtype="<u8", count=ns * nb * 2).reshape(ns, nb, 2)
-    return energies, counts, counters

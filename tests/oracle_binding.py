@@ -6,6 +6,8 @@ import ctypes as C
 import os
 import subprocess
 
+import struct
+
 import numpy as np
 
 from radiative3d_b200 import abi
@@ -96,3 +98,15 @@ def rtcoef(x):
 
 def catch(bin_dt, n_bins, x):
     return _rows(lib().r3d_oracle_catch, 28, 6, x, C.c_double(bin_dt), C.c_uint32(n_bins))
+
+
+def load_bins(path):
+    """Read an "R3DBINS1" result file (written by oracle/ref_harness.cpp)."""
+    with open(path, "rb") as f:
+        if f.read(8) != b"R3DBINS1":
+            raise ValueError(f"{path}: not an R3DBINS1 file")
+        ns, nb = struct.unpack("<II", f.read(8))
+        counters = np.fromfile(f, dtype="<u8", count=abi.R3D_NCOUNTERS)
+        energies = np.fromfile(f, dtype="<f8", count=ns * nb * 5).reshape(ns, nb, 5)
+        counts = np.fromfile(f, dtype="<u8", count=ns * nb * 2).reshape(ns, nb, 2)
+    return energies, counts, counters

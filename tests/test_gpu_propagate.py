@@ -1,0 +1,128 @@
+"""The propagate kernel (through r3d_create / r3d_run / r3d_trace / r3d_fetch) against the reference's own loop.
+
+tests/golden holds end states, bins and counters of the reference's GenerateEventPhonon()+Propagate() run on the
+Philox draw stream; the kernel consumes the same stream, so phonons can be compared one by one.  FP64 rounding
+differs (FMA contraction, CUDA libm), and a trajectory is a chain of up to hundreds of dependent events, so:
+  * discrete outcome (fate, cell, type, move count, draws used) must match for >= 99.5 % of phonons,
+  * for those, time / path length / amplitude / location must match to 1e-8 relative,
+  * bin counts must match except for the phonons above; energies to 1e-8 of the bin.
+"""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from conftest import CONFIGS, REF_HARNESS, dense_bins, load_golden, rel_err
+from radiative3d_b200 import abi, engine
+
+pytestmark = pytest.mark.gpu
+
+
+def compare_finals(fin, ref, frac=0.995, tol=1e-8):
+    same = np.ones(fin.size, dtype=bool)
+    for f in ("moves", "cell", "type", "fate", "draws"):
+        same &= fin[f] == ref[f]
+    assert same.mean() >= frac, f"only {same.mean():.4f} of phonons share the reference's discrete outcome"
+    for f in ("time", "pathlen", "amp"):
+        assert rel_err(fin[f][same], ref[f][same]).max() <= tol, f
+    scale = max(1.0, np.abs(ref["loc"]).max())
+    assert np.abs(fin["loc"][same] - ref["loc"][same]).max() <= tol * scale
+    return same
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_trace_matches_reference(cfg):
+    m, z = load_golden(cfg)
+    n, seed = int(z["run_n"]), int(z["run_seed"])
+    with engine.Engine(m) as eng:
+        fin = eng.trace(n, seed)
+        e, c, k = eng.fetch()
+    ref = z["run_finals"]
+    same = compare_finals(fin, ref)
+    e_ref, c_ref = dense_bins(m, z)
+    n_off = int((~same).sum())
+    # each diverged phonon can move a handful of catches
+    assert np.abs(c.astype(np.int64) - c_ref.astype(np.int64)).sum() <= 50 * n_off
+    if n_off == 0:
+        assert np.array_equal(c, c_ref)
+        assert rel_err(e, e_ref).max() <= 1e-8
+        assert np.array_equal(k[:3], z["run_counters"][:3])
+    assert int(k[abi.R3D_CNT_PHONONS]) == n
+    assert int(k[abi.R3D_CNT_CATCHES]) == int(c.sum())
+    assert int(k[:3].sum()) == n
+
+
+@pytest.mark.parametrize("cfg", ["halfspace", "lopnor"])
+def test_run_equals_trace_and_is_additive(cfg):
+    """Index-keyed RNG: splitting a range across calls must not change counts (energies up to summation order)."""
+    m, z = load_golden(cfg)
+    n = 3000
+    with engine.Engine(m) as eng:
+        eng.run_simulation(n, seed=5)
+        e1, c1, k1 = eng.fetch()
+        eng.reset()
+        eng.run_simulation(1000, seed=5, first_phonon=0)
+        eng.run_simulation(1500, seed=5, first_phonon=1000)
+        eng.run_simulation(500, seed=5, first_phonon=2500)
+        e2, c2, k2 = eng.fetch()
+        eng.reset()
+        e0, c0, k0 = eng.fetch()
+    assert np.array_equal(c1, c2) and np.array_equal(k1[:7], k2[:7])
+    assert rel_err(e1, e2).max() <= 1e-12
+    assert c1.sum() > 0 and c0.sum() == 0 and k0.sum() == 0 and e0.sum() == 0
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_bigger_run_vs_oracle(cfg):
+    """More phonons than the golden fixtures hold, against the oracle (itself pinned to the reference)."""
+    m, _ = load_golden(cfg)
+    n = {"spherical": 1500}.get(cfg, 20000)
+    e_ref, c_ref, k_ref, f_ref = ob.run(m, 100000, n, 99, finals=True, nthreads=4)
+    with engine.Engine(m) as eng:
+        fin = eng.trace(n, seed=99, first_phonon=100000)
+        e, c, k = eng.fetch()
+    same = compare_finals(fin, f_ref)
+    n_off = int((~same).sum())
+    assert np.abs(c.astype(np.int64) - c_ref.astype(np.int64)).sum() <= 50 * n_off
+    tot, tot_ref = e[..., 3:].sum(), e_ref[..., 3:].sum()
+    assert abs(tot - tot_ref) <= (1e-9 + 1e-3 * n_off) * tot_ref
+    # loss / time-out tallies agree up to the diverged phonons
+    assert np.abs(k[:3].astype(np.int64) - k_ref[:3].astype(np.int64)).sum() <= 2 * n_off
+
+
+def test_empty_and_ragged_ranges():
+    m, _ = load_golden("halfspace")
+    with engine.Engine(m) as eng:
+        eng.run_simulation(0)
+        eng.run_simulation(1, first_phonon=2**40)
+        eng.run_simulation(129)
+        t = eng.sync()
+        e, c, k = eng.fetch()
+        assert int(k[abi.R3D_CNT_PHONONS]) == 130 and int(k[:3].sum()) == 130 and t >= 0
+        assert eng.trace(0).size == 0
+        assert eng.launch_count == 2
+
+
+def test_no_deflect_and_no_seismometers():
+    m, _ = load_golden("halfspace")
+    m.no_deflect = 1
+    m.seis = np.zeros(0)
+    e_ref, c_ref, k_ref, f_ref = ob.run(m, 0, 5000, 3, finals=True)
+    with engine.Engine(m) as eng:
+        fin = eng.trace(5000, seed=3)
+        e, c, k = eng.fetch()
+    compare_finals(fin, f_ref)
+    assert e.size == 0 and int(k[abi.R3D_CNT_SCATTERS]) == int(k_ref[abi.R3D_CNT_SCATTERS])
+
+
+def test_device_accumulators_wrap_as_torch():
+    import torch
+    m, _ = load_golden("halfspace_nearsrc50")
+    with engine.Engine(m) as eng:
+        eng.run_simulation(20000, seed=11)
+        eng.sync()
+        e, c, k = eng.fetch()
+        de, dc, dk = (torch.as_tensor(v, device="cuda:0") for v in eng.device_accumulators(0))
+        assert de.dtype == torch.float64 and dc.dtype == torch.int64
+        assert np.array_equal(dc.cpu().numpy().astype(np.uint64).reshape(c.shape), c)
+        assert np.array_equal(de.cpu().numpy().reshape(e.shape), e)
+        assert int(dk[abi.R3D_CNT_PHONONS]) == 20000

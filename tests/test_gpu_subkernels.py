@@ -1,0 +1,128 @@
+"""GPU sub-kernels (through the C ABI's r3d_test_* hooks) against the reference golden vectors and the oracle.
+
+Bar (BASELINE.json north_star): deterministic sub-kernels within 1e-10 relative of the reference's
+double-precision results; cell / face / table indices bit-exact.
+"""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from conftest import CONFIGS, GOLDEN, load_golden, rel_err
+from radiative3d_b200 import engine
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def free():
+    return np.load(f"{GOLDEN}/golden_free.npz")
+
+
+def test_transform(free):
+    out = engine.transform(free["transform_in"])
+    ref = free["transform_out"]
+    # angles: compare as angles (phi, pol wrap at +-pi)
+    d = np.abs(out - ref)
+    d[:, 1:] = np.minimum(d[:, 1:], 2 * np.pi - d[:, 1:])
+    assert d.max() <= TOL * np.pi
+
+
+def test_transform_random_vs_oracle():
+    rng = np.random.default_rng(1)
+    n = 200000
+    x = np.stack([np.arccos(rng.uniform(-1, 1, n)), rng.uniform(-np.pi, np.pi, n), rng.uniform(-np.pi, np.pi, n),
+                  np.arccos(rng.uniform(-1, 1, n)), rng.uniform(-np.pi, np.pi, n), rng.uniform(-np.pi, np.pi, n)], axis=1)
+    out, ref = engine.transform(x), ob.transform(x)
+    # compare the frames, not the angle charts (phi / pol are ill-conditioned next to the poles)
+    def frame(a):
+        st, ct, sp, cp, sr, cr = np.sin(a[:, 0]), np.cos(a[:, 0]), np.sin(a[:, 1]), np.cos(a[:, 1]), np.sin(a[:, 2]), np.cos(a[:, 2])
+        e3 = np.stack([st * cp, st * sp, ct], 1)
+        s1 = np.stack([cr * ct * cp - sr * sp, cr * ct * sp + sr * cp, -cr * st], 1)
+        return e3, s1
+    (e3a, s1a), (e3b, s1b) = frame(out), frame(ref)
+    assert np.abs(e3a - e3b).max() <= TOL and np.abs(s1a - s1b).max() <= TOL
+
+
+def test_rtcoef(free):
+    out = engine.rtcoef(free["rtcoef_in"])
+    ref = free["rtcoef_out"]
+    assert np.array_equal(out[:, 6], ref[:, 6])
+    scale = np.abs(ref[:, :6]).max(axis=1, keepdims=True)
+    assert (np.abs(out[:, :6] - ref[:, :6]) / scale).max() <= TOL
+    assert np.abs(out[:, 7:] - ref[:, 7:]).max() <= TOL
+
+
+def test_rtcoef_builtin_table(free):
+    t = free["rtcoef_test_table"]
+    x = np.zeros((t.shape[0], 15))
+    x[:, 2] = 1.0
+    x[:, 3], x[:, 5] = np.sin(t[:, 1]), np.cos(t[:, 1])
+    x[:, 6:12] = [10, 8, 4, 8, 4, 2]
+    x[:, 12] = t[:, 0]
+    x[:, 14] = 12345
+    out = engine.rtcoef(x)
+    ref = t[:, [3, 5, 7, 4, 6, 8]]
+    scale = np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1e-300)
+    assert (np.abs(out[:, :6] - ref) / scale).max() <= TOL
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_path_and_advance(cfg):
+    m, z = load_golden(cfg)
+    with engine.Engine(m) as eng:
+        out = eng.path_to_boundary(z["path_in"])
+        ref = z["path_out"]
+        assert np.array_equal(out[:, 8], ref[:, 8])               # exit face: bit-exact
+        ok = np.isfinite(ref[:, 0])
+        scale = np.maximum(np.abs(ref[ok, 2:5]).max(), 1.0)
+        assert rel_err(out[ok, 0:2], ref[ok, 0:2]).max() <= 1e-9  # path length / time (differences of near-equal roots)
+        assert np.abs(out[ok, 2:5] - ref[ok, 2:5]).max() <= TOL * scale
+        assert np.abs(out[ok, 5:7] - ref[ok, 5:7]).max() <= 1e-9
+        assert rel_err(out[ok, 7], ref[ok, 7]).max() <= 1e-9
+        assert np.array_equal(np.isfinite(out[:, 0]), ok)
+        out = eng.advance(z["advance_in"])
+        ref = z["advance_out"]
+        assert rel_err(out[:, 0:2], ref[:, 0:2]).max() <= 1e-9
+        assert np.abs(out[:, 2:5] - ref[:, 2:5]).max() <= TOL * scale
+        assert np.abs(out[:, 5:7] - ref[:, 5:7]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+@pytest.mark.parametrize("guide", [0, 1, 3])
+def test_cdf_search_golden(cfg, guide):
+    m, z = load_golden(cfg)
+    nt = m.n_toa
+    for which in range(9):
+        rows = z["cdf_cases"][z["cdf_cases"][:, 0] == which]
+        if which < 4:
+            cdf = m.scat_cdf[which * nt:(which + 1) * nt]
+        elif which < 6:
+            cdf = m.scat_whole_cdf[(which - 4) * 4:(which - 3) * 4]
+        else:
+            cdf = m.src_cdf[(which - 6) * nt:(which - 5) * nt]
+        out = engine.cdf_search(cdf, rows[:, 1].astype(np.uint32), guide)
+        assert np.array_equal(out, rows[:, 2].astype(np.uint32)), (which, guide)
+
+
+@pytest.mark.parametrize("n", [17, 1000, 5242880])
+def test_cdf_search_full_size_vs_oracle(n):
+    """Guide-table search == reference bisection on a table of the scripted size (TOA degree 9), incl. plateaus."""
+    rng = np.random.default_rng(n)
+    w = rng.random(n) ** 8                     # strongly non-uniform weights
+    w[rng.integers(0, n, n // 10)] = 0.0       # zero-probability entries -> flat stretches in the CDF
+    cdf = np.cumsum(w)
+    k = np.concatenate([rng.integers(0, 2**31, 300000, dtype=np.uint32), np.array([0, 1, 2**31 - 1, 2**31 - 2, 2**30], dtype=np.uint32)])
+    ref = ob.cdf_search(cdf, k)
+    for guide in (0, 1, 8, 20):
+        assert np.array_equal(engine.cdf_search(cdf, k, guide), ref), guide
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_catch(cfg):
+    m, z = load_golden(cfg)
+    out = engine.catch(m.bin_dt, m.n_bins, z["catch_in"])
+    ref = ob.catch(m.bin_dt, m.n_bins, z["catch_in"])            # oracle == golden (test_oracle_golden), exact energies
+    assert np.array_equal(out[:, :2], ref[:, :2])
+    assert np.array_equal(out[:, :2], z["catch_out"][:, :2])
+    assert rel_err(out[:, 2:], ref[:, 2:]).max() <= TOL
