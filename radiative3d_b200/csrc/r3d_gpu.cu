@@ -578,13 +578,13 @@ int build_device(DevState &D, const r3d_model_desc *d, int guide_bits_req) {
   }
 
   // accumulators
-  const size_t nb = (size_t)d->n_seis * d->n_bins;
+  const size_t nb = std::max<size_t>((size_t)d->n_seis * d->n_bins, 1);
   if (int rc = dev_alloc(D, &M.energies, nb * R3D_BIN_NF64)) return rc;
   if (int rc = dev_alloc(D, &M.counts, nb * R3D_BIN_NCNT)) return rc;
   if (int rc = dev_alloc(D, &M.counters, (size_t)R3D_NCOUNTERS)) return rc;
   if (int rc = dev_alloc(D, &M.next_phonon, (size_t)1)) return rc;
-  CK(cudaMemsetAsync(M.energies, 0, std::max<size_t>(nb, 1) * R3D_BIN_NF64 * sizeof(double), D.stream));
-  CK(cudaMemsetAsync(M.counts, 0, std::max<size_t>(nb, 1) * R3D_BIN_NCNT * sizeof(unsigned long long), D.stream));
+  CK(cudaMemsetAsync(M.energies, 0, nb * R3D_BIN_NF64 * sizeof(double), D.stream));
+  CK(cudaMemsetAsync(M.counts, 0, nb * R3D_BIN_NCNT * sizeof(unsigned long long), D.stream));
   CK(cudaMemsetAsync(M.counters, 0, R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
 
   // launch geometry: persistent grid, a whole number of resident CTAs per SM

@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""Scratch: one warm-up launch + one measured launch of the propagate kernel, for ncu.
+usage: profile_target.py <config> <toa degree> <n phonons>   (model built by the oracle/_ref harness)"""
+import os
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import ref_configs  # noqa: E402
+from radiative3d_b200 import abi, engine  # noqa: E402
+from radiative3d_b200.model import FlatModel  # noqa: E402
+
+cfg, deg, n = sys.argv[1], int(sys.argv[2]), int(float(sys.argv[3]))
+with tempfile.TemporaryDirectory() as tmp:
+    env = dict(os.environ, R3D_HARNESS="dump", R3D_HARNESS_OUT=os.path.join(tmp, "m"))
+    subprocess.run([os.path.join(ROOT, "oracle/_ref/r3d_ref_harness")] + ref_configs.cmdline(cfg, 10, deg, tmp), cwd=tmp,
+                   env=env, check=True, capture_output=True)
+    m = FlatModel.load(os.path.join(tmp, "m"))
+eng = engine.Engine(m)
+eng.run_simulation(n, seed=1)
+eng.sync()
+eng.reset()
+eng.run_simulation(n, seed=2)
+t = eng.sync()
+e, c, k = eng.fetch()
+print(f"{cfg} deg {deg} n={n}: {t * 1e3:.2f} ms, {n / t:.3e} phonons/s, {int(k[abi.R3D_CNT_EVENTS]) / t:.3e} events/s")

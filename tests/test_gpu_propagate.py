@@ -17,13 +17,23 @@ from radiative3d_b200 import abi, engine
 pytestmark = pytest.mark.gpu
 
 
+def bin_energy_err(e, e_ref):
+    """Largest |difference| of any energy channel relative to its bin's total energy (axis components of a bin
+    can be exactly 0 in the reference and 1e-35 on the device)."""
+    scale = np.maximum(e_ref[..., 3:].sum(axis=-1, keepdims=True), 1e-300)
+    return (np.abs(e - e_ref) / scale).max()
+
+
 def compare_finals(fin, ref, frac=0.995, tol=1e-8):
     same = np.ones(fin.size, dtype=bool)
     for f in ("moves", "cell", "type", "fate", "draws"):
         same &= fin[f] == ref[f]
     assert same.mean() >= frac, f"only {same.mean():.4f} of phonons share the reference's discrete outcome"
-    for f in ("time", "pathlen", "amp"):
+    for f in ("time", "pathlen"):
         assert rel_err(fin[f][same], ref[f][same]).max() <= tol, f
+    # amplitude = exp(-pi f sum(t/Q)): its relative error is the ABSOLUTE error of an exponent of size |ln amp|
+    la, lr = np.log(fin["amp"][same]), np.log(ref["amp"][same])
+    assert (np.abs(la - lr) <= tol * (1.0 + np.abs(lr))).all(), "amp"
     scale = max(1.0, np.abs(ref["loc"]).max())
     assert np.abs(fin["loc"][same] - ref["loc"][same]).max() <= tol * scale
     return same
@@ -44,7 +54,7 @@ def test_trace_matches_reference(cfg):
     assert np.abs(c.astype(np.int64) - c_ref.astype(np.int64)).sum() <= 50 * n_off
     if n_off == 0:
         assert np.array_equal(c, c_ref)
-        assert rel_err(e, e_ref).max() <= 1e-8
+        assert bin_energy_err(e, e_ref) <= 1e-8
         assert np.array_equal(k[:3], z["run_counters"][:3])
     assert int(k[abi.R3D_CNT_PHONONS]) == n
     assert int(k[abi.R3D_CNT_CATCHES]) == int(c.sum())
@@ -67,7 +77,7 @@ def test_run_equals_trace_and_is_additive(cfg):
         eng.reset()
         e0, c0, k0 = eng.fetch()
     assert np.array_equal(c1, c2) and np.array_equal(k1[:7], k2[:7])
-    assert rel_err(e1, e2).max() <= 1e-12
+    assert bin_energy_err(e1, e2) <= 1e-12
     assert c1.sum() > 0 and c0.sum() == 0 and k0.sum() == 0 and e0.sum() == 0
 
 
