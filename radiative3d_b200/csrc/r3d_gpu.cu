@@ -1,15 +1,10 @@
-// r3d_gpu.cu -- propagate kernels and the C ABI of include/r3d_gpu.h (sm_100a only).
+// r3d_gpu.cu -- the C ABI of include/r3d_gpu.h and the host side of the propagate path (sm_100a only).
 //
-// One phonon per thread.  A warp keeps all 32 lanes busy by refilling dead lanes from a
-// per-launch work counter (chunked, one atomic per warp per 128 phonons); each loop
-// iteration is one iteration of the reference's Propagate loop (phonons.cpp:542) for every
-// live lane, arranged in three phases so that the expensive, latency-bound CDF search is
-// executed once per iteration for every lane that needs one -- whether it is a freshly
-// generated source phonon (sources.cpp:156-170) or a scatter draw (scatterers.cpp:318-363):
-//   A  refill / time-out + validity / distance to boundary / path-length draw / boundary work
-//   B  CDF search + take-off-angle fetch            (lanes with a draw request)
-//   C  new-phonon init, or Phonon::Transform
-// There is no CPU fallback anywhere in this file.
+// The device work is in r3d_wavefront.cuh (three kernels per step over a pool of phonons in HBM) and
+// r3d_device.cuh (the physics).  This file uploads a flattened model, builds the exact guide tables for the
+// CDF searches, and drives the step loop: every device of a handle has one worker thread that enqueues
+// batches of steps on the device's stream and polls a device flag between batches, so r3d_run() returns at
+// once and devices run concurrently.  There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -17,14 +12,17 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <deque>
+#include <stdlib.h>
 #include "r3d_gpu.h"
 #include "r3d_device.cuh"
+#include "r3d_wavefront.cuh"
 
 using namespace r3d;
 
-#define R3D_THREADS 128
-#define R3D_CHUNK 128ull
-#define FULL 0xffffffffu
 
 namespace {
 
@@ -37,300 +35,6 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
       return fail(e_ == cudaErrorMemoryAllocation ? R3D_ENOMEM : R3D_ECUDA,                        \
                   std::string(#call) + ": " + cudaGetErrorString(e_));                             \
   } while (0)
-
-// ---------------------------------------------------------------------------
-// phonon state (phonons.hpp:69-126), register resident
-// ---------------------------------------------------------------------------
-struct Phonon {
-  double time, pathlen, recent, amp;
-  v3 loc;
-  double th, ph, pol;
-  uint32_t moves, cell;
-  int type;
-};
-
-R3D_DEV void move(Phonon &p, const Travel &t) {   // Phonon::Move, phonons.cpp:62-70
-  p.pathlen += t.len; p.time += t.time; p.recent += t.time;
-  p.loc = t.loc; p.th = t.th; p.ph = t.ph;
-  p.amp *= t.atten; p.moves += 1;
-}
-
-// Phonon::Refraction_FullRT (phonons.cpp:429-476) + CellFace::GetRTBasis (media_cellface.cpp:122-149)
-template <class Cell>
-R3D_DEV void refraction_fullrt(const DevModel &M, const double *cells, Phonon &p, int face, bool adjoin, uint32_t other, Rng &g) {
-  const double *c = cells + (size_t)p.cell * M.cell_nparam;
-  RTCoef rt;
-  rt.init(Cell::normal(c, face, p.loc), from_thph(p.th, p.ph));
-  rt.densR = Cell::dens(c, p.loc);
-  rt.velR[0] = Cell::veloc(c, 0, p.loc);
-  rt.velR[1] = Cell::veloc(c, 1, p.loc);
-  if (adjoin) {
-    const double *o = cells + (size_t)other * M.cell_nparam;
-    rt.densT = Cell::dens(o, p.loc);
-    rt.velT[0] = Cell::veloc(o, 0, p.loc);
-    rt.velT[1] = Cell::veloc(o, 1, p.loc);
-  } else {                                    // free surface
-    rt.densT = 0.0; rt.velT[0] = 1e-12; rt.velT[1] = 1e-12; rt.notransmit = true;
-  }
-  int intype = R3D_RAY_P;
-  if (p.type == R3D_RAY_S) intype = rt.choose_spol(dir_of_motion(p.type, p.th, p.ph, p.pol), g.next());
-  rt.get_coefs(intype);
-  rt.choose(g.next());
-  const bool reflected = (rt.choice == R_P || rt.choice == R_SV || rt.choice == R_SH);
-  v3 outdir = rt.chosen_ray_dir();
-  p.type = (rt.choice == R_P || rt.choice == T_P) ? R3D_RAY_P : R3D_RAY_S;
-  p.th = xyz_theta(outdir); p.ph = xyz_phi(outdir);
-  if (p.type == R3D_RAY_S) {
-    v3 pdomo = rt.chosen_pdom();
-    p.pol = atan2(dot(pdomo, thph_phihat(p.ph)), dot(pdomo, thph_thetahat(p.th, p.ph)));
-  }
-  if (!reflected) p.cell = other;
-}
-
-// Phonon::Refraction_Bend (phonons.cpp:311-405)
-template <class Cell>
-R3D_DEV void refraction_bend(const DevModel &M, const double *cells, Phonon &p, int face, uint32_t other) {
-  const double *c = cells + (size_t)p.cell * M.cell_nparam;
-  const double *o = cells + (size_t)other * M.cell_nparam;
-  v3 mdir = from_thph(p.th, p.ph);
-  v3 fnorm = Cell::normal(c, face, p.loc);
-  v3 fpara = inplane_unit_perp(fnorm, mdir);
-  v3 fparash = cross(fnorm, fpara);
-  double veli = Cell::veloc(c, p.type, p.loc), velo = Cell::veloc(o, p.type, p.loc);
-  double sini = dot(fpara, mdir);
-  double sino = (velo / veli) * sini;
-  bool transfer; double coso;
-  if (sino >= 1.0) { transfer = false; sino = sini; coso = -1.0 * dot(fnorm, mdir); }
-  else { transfer = true; coso = sqrt(1.0 - (sino * sino)); }
-  v3 outdir = add(scal(fpara, sino), scal(fnorm, coso));
-  double polout = 0;
-  if (p.type != R3D_RAY_P) {
-    v3 pdomi = dir_of_motion(p.type, p.th, p.ph, p.pol);
-    v3 svbasei = cross(fparash, mdir), svbaseo = cross(fparash, outdir);
-    double shcomi = dot(pdomi, fparash), svcomi = dot(pdomi, svbasei);
-    v3 pdomo = add(scal(fparash, shcomi), scal(svbaseo, svcomi));
-    polout = atan2(dot(pdomo, xyz_phihat(outdir)), dot(pdomo, xyz_thetahat(outdir)));
-  }
-  p.th = xyz_theta(outdir); p.ph = xyz_phi(outdir);
-  p.pol = polout;
-  if (transfer) p.cell = other;
-}
-
-// CellFace::VelocityJump (media_cellface.cpp:83-99)
-template <class Cell>
-R3D_DEV double velocity_jump(const DevModel &M, const double *cells, uint32_t cell, uint32_t other, v3 loc) {
-  const double *c = cells + (size_t)cell * M.cell_nparam, *o = cells + (size_t)other * M.cell_nparam;
-  double v1 = Cell::veloc(c, 0, loc), v2 = Cell::veloc(o, 0, loc);
-  double dvp = fabs(2 * (v2 - v1) / (v2 + v1));
-  v1 = Cell::veloc(c, 1, loc); v2 = Cell::veloc(o, 1, loc);
-  double dvs = fabs(2 * (v2 - v1) / (v2 + v1));
-  return (dvp > dvs) ? dvp : dvs;
-}
-
-// DataReporter::ReportPhononCollected (dataout.cpp:545-568): every seismometer is pass-through
-// (dataout.cpp:50), so all of them are tested.  A conservative squared-distance pre-filter on a
-// shared-memory (x,y,z,r_out^2) record skips the exact test for seismometers that cannot catch.
-template <class Cell>
-R3D_DEV uint32_t collect(const DevModel &M, const double *cells, const double4 *sph, const Phonon &p) {
-  const double *c = cells + (size_t)p.cell * M.cell_nparam;
-  const double vel = Cell::veloc(c, p.type, p.loc);
-  const v3 dir = from_thph(p.th, p.ph);
-  const v3 dopm = dir_of_motion(p.type, p.th, p.ph, p.pol);
-  uint32_t n = 0;
-  for (uint32_t s = 0; s < M.n_seis; s++) {
-    double4 q = sph[s];
-    double dx = q.x - p.loc.x, dy = q.y - p.loc.y, dz = q.z - p.loc.z;
-    if (dx * dx + dy * dy + dz * dz > q.w) continue;
-    uint32_t bin; double e[4];
-    if (seis_catch(M.seis + (size_t)s * R3D_SEIS_NPARAM, M.bin_dt, M.n_bins, p.time, p.loc, dir, dopm, p.type, p.amp, vel, bin, e)) {
-      size_t b = (size_t)s * M.n_bins + bin;
-      atomicAdd(M.energies + b * 5 + 0, e[0]);
-      atomicAdd(M.energies + b * 5 + 1, e[1]);
-      atomicAdd(M.energies + b * 5 + 2, e[2]);
-      atomicAdd(M.energies + b * 5 + 3 + p.type, e[3]);
-      atomicAdd(M.counts + b * 2 + p.type, 1ull);
-      n++;
-    }
-  }
-  return n;
-}
-
-R3D_DEV void write_final(r3d_phonon_final *f, const Phonon &p, uint32_t fate, const Rng &g, uint32_t catches, uint32_t scatters, uint32_t iters) {
-  f->time = p.time; f->pathlen = p.pathlen; f->amp = p.amp;
-  f->loc[0] = p.loc.x; f->loc[1] = p.loc.y; f->loc[2] = p.loc.z;
-  f->theta = p.th; f->phi = p.ph; f->pol = p.pol;
-  f->moves = p.moves; f->cell = p.cell; f->type = (uint32_t)p.type; f->fate = fate;
-  f->draws = g.ordinal; f->catches = catches; f->scatters = scatters; f->iters = iters;
-}
-
-// ---------------------------------------------------------------------------
-// the propagate kernel
-// ---------------------------------------------------------------------------
-template <class Cell, bool TRACE>
-__global__ void __launch_bounds__(R3D_THREADS)
-propagate_kernel(const DevModel M, unsigned long long first, unsigned long long n, unsigned long long seed,
-                 int cells_in_smem, r3d_phonon_final *finals) {
-  extern __shared__ double4 smem4[];
-  double4 *sph = smem4;                                       // [n_seis]
-  double *scells = reinterpret_cast<double *>(smem4 + M.n_seis);
-  for (uint32_t i = threadIdx.x; i < M.n_seis; i += blockDim.x) sph[i] = M.seis_sphere[i];
-  if (cells_in_smem)
-    for (uint32_t i = threadIdx.x; i < M.n_cells * M.cell_nparam; i += blockDim.x) scells[i] = M.cell_params[i];
-  __syncthreads();
-  const double *cells = cells_in_smem ? scells : M.cell_params;
-
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  Phonon p;
-  Rng g;
-  bool alive = false, done = false;
-  unsigned long long idx = 0, wnext = 0, wend = 0;
-  uint32_t ph_catches = 0, ph_scatters = 0, ph_iters = 0;
-  // per-thread tallies (dataout.cpp:591-617)
-  unsigned long long n_lost = 0, n_timeout = 0, n_invalid = 0, n_events = 0, n_catches = 0, n_scatters = 0, n_phonons = 0;
-  uint32_t diag = 0;
-  g.init(seed, 0);
-  p.time = p.pathlen = p.recent = p.amp = 0; p.loc = V(0, 0, 0); p.th = p.ph = p.pol = 0; p.moves = 0; p.cell = 0; p.type = 0;
-
-  for (;;) {
-    int req = 0;                 // 0 none, 1 source take-off angle, 2 scatter angle
-    const double *rcdf = nullptr; const uint32_t *rguide = nullptr; uint32_t rk = 0, conv = 0;
-
-    // ---- phase A.0: refill dead lanes --------------------------------------
-    const bool need = !alive && !done;
-    const unsigned needmask = __ballot_sync(FULL, need);
-    if (needmask) {
-      if (wnext >= wend) {                                   // warp-uniform
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(M.next_phonon, R3D_CHUNK);
-        base = __shfl_sync(FULL, base, 0);
-        wnext = (base < n) ? base : n;
-        wend = (base + R3D_CHUNK < n) ? base + R3D_CHUNK : n;
-      }
-      if (need) {
-        unsigned long long cand = wnext + __popc(needmask & lt_mask);
-        if (cand < wend) {
-          // ShearDislocation::GenerateEventPhonon (events.cpp:111-124)
-          idx = first + cand;
-          g.init(seed, idx);
-          uint32_t rt3 = cdf_search_small(M.src_whole, 3, g.next());
-          rcdf = M.src_cdf + (size_t)rt3 * M.n_toa;
-          rguide = M.src_guide + (size_t)rt3 * M.guide_stride;
-          rk = g.next();
-          req = 1;
-          p.time = 0; p.pathlen = 0; p.recent = 0; p.moves = 0; p.amp = 1.0;       // phonons.hpp:193-207
-          p.loc = V(M.src_loc[0], M.src_loc[1], M.src_loc[2]);
-          p.cell = M.src_cell;
-          p.pol = (rt3 == R3D_RAY_SH) ? kPi * 0.5 : 0.0;
-          p.type = (rt3 == R3D_RAY_P) ? R3D_RAY_P : R3D_RAY_S;
-          ph_catches = ph_scatters = ph_iters = 0;
-          n_phonons++;
-        } else if (wend >= n) {
-          done = true;
-        }
-      }
-      unsigned long long adv = wnext + __popc(needmask);
-      wnext = (adv < wend) ? adv : wend;
-    }
-    if (__all_sync(FULL, done && !alive)) break;
-
-    // ---- phase A: one Propagate-loop iteration (phonons.cpp:542-679) ---------
-    if (alive) {
-      uint32_t fate = 0;
-      n_events++; ph_iters++;
-      if (p.time > M.ttl) fate = R3D_FATE_TIMEOUT;
-      else if ((p.moves % 128u) == 127u) {                   // phonons.cpp:554-584
-        int why = -1;
-        if (isnan(p.pathlen)) why = R3D_INV_PATH_NAN;
-        else if (isnan(p.time)) why = R3D_INV_TIME_NAN;
-        else if (p.pathlen < 0) why = R3D_INV_PATH_NEGATIVE;
-        else if ((p.time < 0) || (p.recent < 0)) why = R3D_INV_TIME_NEGATIVE;
-        else if (p.recent == 0) why = R3D_INV_STUCK;
-        else if (p.recent < M.slow_concern) why = R3D_INV_SLOW;
-        else if (p.moves > M.loop_concern) why = R3D_INV_LOOP_EXCEED;
-        if (why >= 0) fate = R3D_FATE_INVALID | ((1u << why) << 8);
-        else p.recent = 0;
-      }
-      if (!fate) {
-        const double *c = cells + (size_t)p.cell * M.cell_nparam;
-        typename Cell::Path P;
-        const double edgelen = Cell::path(M, c, p.type, p.loc, p.th, p.ph, P);
-        if (edgelen == pinf()) fate = R3D_FATE_TIMEOUT;       // phonons.cpp:595-598
-        else {
-          const uint32_t scat = __ldg(M.cell_scat + p.cell);
-          // Scatterer::GetRandomPathLength (scatterers.cpp:297-307)
-          double r = 1.0 - ((double)g.next()) / (kRandMax + 1);
-          const double scatlen = -log(r) * __ldg(M.scat_mfp + scat * 2 + p.type);
-          if (scatlen < edgelen) {
-            Travel tr = Cell::advance(M, c, p.type, scatlen, p.loc, p.th, p.ph, P);
-            move(p, tr);
-            // Scatterer::GetRandomScatteredRelativePhonon (scatterers.cpp:318-363)
-            if (M.no_deflect) {
-              transform(p.th, p.ph, p.pol, M.min_theta, 0.0, 0.0);
-              n_scatters++; ph_scatters++;
-            } else {
-              conv = cdf_search_small(M.scat_whole + (scat * 2 + p.type) * 4, 4, g.next());
-              rcdf = M.scat_cdf + ((size_t)scat * 4 + conv) * M.n_toa;
-              rguide = M.scat_guide + ((size_t)scat * 4 + conv) * M.guide_stride;
-              rk = g.next();
-              req = 2;
-            }
-          } else {
-            Travel tr = Cell::advance(M, c, p.type, edgelen, p.loc, p.th, p.ph, P);
-            move(p, tr);
-            const uint32_t fi = p.cell * M.faces_per_cell + P.face;
-            const uint32_t fl = __ldg(M.face_flags + fi);
-            const uint32_t other = __ldg(M.face_other + fi);
-            if (fl & R3D_FACE_COLLECT) {
-              uint32_t k = collect<Cell>(M, cells, sph, p);
-              n_catches += k; ph_catches += k;
-            }
-            if (fl & R3D_FACE_REFLECT) refraction_fullrt<Cell>(M, cells, p, P.face, (fl & R3D_FACE_ADJOIN) != 0, other, g);
-            else if (fl & R3D_FACE_ADJOIN) {                 // Phonon::Refract, phonons.cpp:225-255
-              if (fl & R3D_FACE_DISCON) refraction_fullrt<Cell>(M, cells, p, P.face, true, other, g);
-              else if (velocity_jump<Cell>(M, cells, p.cell, other, p.loc) > 0.00001) refraction_bend<Cell>(M, cells, p, P.face, other);
-              else p.cell = other;                           // Refraction_Continuous
-            } else fate = R3D_FATE_LOST;
-          }
-        }
-      }
-      if (fate) {
-        alive = false;
-        switch (fate & 0xFF) {
-          case R3D_FATE_LOST: n_lost++; break;
-          case R3D_FATE_TIMEOUT: n_timeout++; break;
-          default: n_invalid++; diag |= (fate >> 8); break;
-        }
-        if (TRACE) write_final(finals + (idx - first), p, fate, g, ph_catches, ph_scatters, ph_iters);
-      }
-    }
-
-    // ---- phase B + C: CDF search, take-off angle, new direction ------------------
-    if (req) {
-      const uint32_t ti = cdf_search(rcdf, M.n_toa, rguide, M.guide_shift, rk);
-      const double2 t = __ldg(M.toa + ti);
-      if (req == 1) { p.th = t.x; p.ph = t.y; alive = true; }
-      else {
-        const uint32_t scat = __ldg(M.cell_scat + p.cell);
-        const double rpol = (conv == 3) ? __ldg(M.scat_spol + (size_t)scat * M.n_toa + ti) : 0.0;
-        transform(p.th, p.ph, p.pol, t.x, t.y, rpol);
-        p.type = (int)(conv & 1u);                            // PP,PS,SP,SS -> P,S,P,S
-        n_scatters++; ph_scatters++;
-      }
-    }
-  }
-
-  // ---- tallies: warp reduce, one atomic per warp and counter ----------------------
-  unsigned long long t[7] = {n_lost, n_timeout, n_invalid, n_events, n_catches, n_scatters, n_phonons};
-#pragma unroll
-  for (int k = 0; k < 7; k++) {
-    unsigned long long v = t[k];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
-    if (lane == 0 && v) atomicAdd(M.counters + k, v);
-  }
-  diag = __reduce_or_sync(FULL, diag);
-  if (lane == 0 && diag) atomicOr(M.counters + 7, (unsigned long long)diag);
-}
 
 // ---------------------------------------------------------------------------
 // model-preparation kernels
@@ -364,6 +68,21 @@ __global__ void seis_sphere_kernel(const double *seis, uint32_t n, double4 *out)
   const double *s = seis + (size_t)i * R3D_SEIS_NPARAM;
   double ro = fmax(s[14], s[15]);
   out[i] = make_double4(s[0], s[1], s[2], ro * ro * (1.0 + 1e-12));   // d^2 > w  =>  sqrt(d^2) > r_out for both types
+}
+
+// counters[k] = sum (OR for the diagnostic word) over the per-block tally rows
+__global__ void reduce_tally_kernel(const unsigned long long *rows, uint32_t n_rows, unsigned long long *counters) {
+  __shared__ unsigned long long sm[256];
+  const int k = blockIdx.x;
+  unsigned long long x = 0;
+  for (uint32_t r = threadIdx.x; r < n_rows; r += blockDim.x) { if (k == 7) x |= rows[(size_t)r * R3D_NCOUNTERS + k]; else x += rows[(size_t)r * R3D_NCOUNTERS + k]; }
+  sm[threadIdx.x] = x;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { if (k == 7) sm[threadIdx.x] |= sm[threadIdx.x + o]; else sm[threadIdx.x] += sm[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counters[k] = sm[0];
 }
 
 // ---------------------------------------------------------------------------
@@ -428,23 +147,39 @@ __global__ void test_catch_kernel(double bin_dt, uint32_t n_bins, const double *
 // ---------------------------------------------------------------------------
 // host side of the handle
 // ---------------------------------------------------------------------------
+struct JobReq { unsigned long long first, n, seed; r3d_phonon_final *finals; };
+
 struct DevState {
   int device = -1;
   cudaStream_t stream = nullptr;
   DevModel M;
+  Pool Q;
+  uint32_t cell_kind = 0;
   std::vector<void *> allocs;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;   // one pair per r3d_run since the last sync
-  int grid = 0;
-  size_t smem = 0;
+  int gridA = 0, gridB = 0, gridC = 0;
+  size_t smemA = 0, smemC = 0;
   int cells_in_smem = 0;
+  uint32_t n_tally_rows = 0;
+  uint32_t *h_flag = nullptr;              // pinned
+  int steps_per_batch = 16;
+  // worker thread: runs the step loop of queued jobs on this device's stream
+  std::thread worker;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<JobReq> jobs;
+  bool stop = false;
+  bool busy = false;
+  int err_code = 0;
+  std::string err;
+  double seconds = 0;                      // device time of the jobs finished since the last r3d_sync
+  unsigned long long launches = 0, steps = 0;
 };
 
 }  // namespace
 
 struct r3d_handle {
-  std::vector<DevState> devs;
+  std::vector<DevState *> devs;
   uint32_t cell_kind = 0, n_seis = 0, n_bins = 0;
-  unsigned long long launches = 0;
 };
 
 namespace {
@@ -466,14 +201,24 @@ int dev_upload(DevState &D, const T **p, const T *host, size_t count) {
   return 0;
 }
 
-typedef void (*propagate_fn)(const DevModel, unsigned long long, unsigned long long, unsigned long long, int, r3d_phonon_final *);
-propagate_fn pick_kernel(uint32_t kind, bool trace) {
+typedef void (*advance_fn)(const DevModel, const Pool, const Job, int);
+typedef void (*draw_fn)(const DevModel, const Pool, uint32_t);
+typedef void (*interface_fn)(const DevModel, const Pool, const Job, int, uint32_t);
+advance_fn pick_advance(uint32_t kind, bool trace) {
   switch (kind) {
-    case R3D_CELL_CYLINDER: return trace ? propagate_kernel<Cylinder, true> : propagate_kernel<Cylinder, false>;
-    case R3D_CELL_SHELL: return trace ? propagate_kernel<Shell, true> : propagate_kernel<Shell, false>;
-    default: return trace ? propagate_kernel<Tetra, true> : propagate_kernel<Tetra, false>;
+    case R3D_CELL_CYLINDER: return trace ? advance_kernel<Cylinder, true> : advance_kernel<Cylinder, false>;
+    case R3D_CELL_SHELL: return trace ? advance_kernel<Shell, true> : advance_kernel<Shell, false>;
+    default: return trace ? advance_kernel<Tetra, true> : advance_kernel<Tetra, false>;
   }
 }
+interface_fn pick_interface(uint32_t kind, bool trace) {
+  switch (kind) {
+    case R3D_CELL_CYLINDER: return trace ? interface_kernel<Cylinder, true> : interface_kernel<Cylinder, false>;
+    case R3D_CELL_SHELL: return trace ? interface_kernel<Shell, true> : interface_kernel<Shell, false>;
+    default: return trace ? interface_kernel<Tetra, true> : interface_kernel<Tetra, false>;
+  }
+}
+draw_fn pick_draw(bool trace) { return trace ? draw_kernel<true> : draw_kernel<false>; }
 
 int validate(const r3d_model_desc *d) {
   if (!d) return fail(R3D_EINVAL, "null model descriptor");
@@ -492,6 +237,7 @@ int validate(const r3d_model_desc *d) {
   if (d->cell_nparam != np || d->faces_per_cell != nf) return fail(R3D_EINVAL, "cell_nparam / faces_per_cell do not match cell_kind");
   if (d->src_cell >= d->n_cells) return fail(R3D_EINVAL, "src_cell out of range");
   if (!(d->bin_dt > 0) || !d->n_bins) return fail(R3D_EINVAL, "bin_dt and n_bins must be positive");
+  if ((uint64_t)d->n_scat * 4 > 0xffffffffull) return fail(R3D_EINVAL, "too many scatterers");
   for (uint32_t i = 0; i < d->n_cells; i++) {
     if (d->cell_scat[i] >= d->n_scat) return fail(R3D_EINVAL, "cell_scat out of range");
     for (uint32_t f = 0; f < nf; f++)
@@ -506,9 +252,15 @@ int validate(const r3d_model_desc *d) {
   return 0;
 }
 
-int build_device(DevState &D, const r3d_model_desc *d, int guide_bits_req) {
+int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+int build_device(DevState &D, const r3d_model_desc *d) {
   CK(cudaSetDevice(D.device));
   CK(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
+  D.cell_kind = d->cell_kind;
   DevModel &M = D.M;
   memset(&M, 0, sizeof M);
   M.freq_hz = d->freq_hz; M.ttl = d->ttl; M.bin_dt = d->bin_dt;
@@ -520,7 +272,7 @@ int build_device(DevState &D, const r3d_model_desc *d, int guide_bits_req) {
   M.cell_nparam = d->cell_nparam; M.faces_per_cell = d->faces_per_cell;
   const size_t nt = d->n_toa, ns = d->n_scat, nc = d->n_cells, nf = d->faces_per_cell;
 
-  // take-off angles, packed (theta, phi) with the constructor's theta clamp applied
+  // take-off angles, packed (theta, phi) with the Phonon constructor's theta clamp applied
   const double *th = nullptr, *ph = nullptr;
   if (int rc = dev_upload(D, &th, d->toa_theta, nt)) return rc;
   if (int rc = dev_upload(D, &ph, d->toa_phi, nt)) return rc;
@@ -553,7 +305,7 @@ int build_device(DevState &D, const r3d_model_desc *d, int guide_bits_req) {
   int hbad = 0;
   CK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, D.stream));
   CK(cudaStreamSynchronize(D.stream));
-  int bits = guide_bits_req;
+  int bits = env_int("R3D_GUIDE_BITS", -1);
   if (bits < 0) {                         // default: about 4 table entries per bucket
     bits = 0;
     while ((1ull << (bits + 2)) < nt && bits < 24) bits++;
@@ -587,56 +339,170 @@ int build_device(DevState &D, const r3d_model_desc *d, int guide_bits_req) {
   CK(cudaMemsetAsync(M.counts, 0, nb * R3D_BIN_NCNT * sizeof(unsigned long long), D.stream));
   CK(cudaMemsetAsync(M.counters, 0, R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
 
-  // launch geometry: persistent grid, a whole number of resident CTAs per SM
+  // launch geometry: grid-stride kernels sized to a whole number of resident CTAs per SM
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, D.device));
-  size_t cell_bytes = nc * d->cell_nparam * sizeof(double);
+  const size_t cell_bytes = nc * d->cell_nparam * sizeof(double);
   D.cells_in_smem = cell_bytes <= 16 * 1024;
-  D.smem = (size_t)d->n_seis * sizeof(double4) + (D.cells_in_smem ? cell_bytes : 0);
-  if (D.smem > (size_t)prop.sharedMemPerBlockOptin)
+  D.smemA = D.cells_in_smem ? cell_bytes : 0;
+  D.smemC = (size_t)d->n_seis * sizeof(double4) + (D.cells_in_smem ? cell_bytes : 0);
+  if (D.smemC > (size_t)prop.sharedMemPerBlockOptin)
     return fail(R3D_EUNSUPPORTED, "too many seismometers for the shared-memory scan table");
-  int per_sm = 1;
+  int occA = 1, occB = 1, occC = 1;
   for (int trace = 0; trace < 2; trace++) {
-    propagate_fn fn = pick_kernel(d->cell_kind, trace != 0);
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, R3D_THREADS, D.smem));
-    if (trace == 0) per_sm = std::max(occ, 1);
+    advance_fn fa = pick_advance(d->cell_kind, trace != 0);
+    interface_fn fc = pick_interface(d->cell_kind, trace != 0);
+    CK(cudaFuncSetAttribute(fa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smemA));
+    CK(cudaFuncSetAttribute(fc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smemC));
+    if (trace == 0) {
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, fa, R3D_A_THREADS, D.smemA));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, pick_draw(false), R3D_B_THREADS, 0));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occC, fc, R3D_C_THREADS, D.smemC));
+    }
   }
-  D.grid = prop.multiProcessorCount * per_sm;
+  const int sms = prop.multiProcessorCount;
+  D.gridA = sms * std::max(occA, 1);
+  D.gridB = sms * std::max(occB, 1);
+  D.gridC = sms * std::max(occC, 1);
+
+  // the pool
+  Pool &Q = D.Q;
+  memset(&Q, 0, sizeof Q);
+  long slots = env_int("R3D_POOL_SLOTS", 1 << 21);
+  if (slots < 256) slots = 256;
+  slots = (slots + 255) / 256 * 256;
+  Q.n_slots = (uint32_t)slots;
+  const size_t P = Q.n_slots;
+  double **dbl[] = {&Q.time, &Q.pathlen, &Q.recent, &Q.amp, &Q.lx, &Q.ly, &Q.lz, &Q.th, &Q.ph, &Q.pol};
+  for (double **a : dbl) if (int rc = dev_alloc(D, a, P)) return rc;
+  uint32_t **u32[] = {&Q.moves, &Q.cell, &Q.ordinal, &Q.tr_catches, &Q.tr_scatters, &Q.tr_iters};
+  for (uint32_t **a : u32) if (int rc = dev_alloc(D, a, P)) return rc;
+  if (int rc = dev_alloc(D, &Q.type, P)) return rc;
+  if (int rc = dev_alloc(D, &Q.alive, P)) return rc;
+  if (int rc = dev_alloc(D, &Q.idx, P)) return rc;
+  if (int rc = dev_alloc(D, &Q.q_draw, P)) return rc;
+  if (int rc = dev_alloc(D, &Q.q_face, P)) return rc;
+  if (int rc = dev_alloc(D, &Q.q_count, (size_t)4)) return rc;
+  D.n_tally_rows = (uint32_t)(D.gridA + D.gridB + D.gridC);
+  if (int rc = dev_alloc(D, &Q.block_tally, (size_t)D.n_tally_rows * R3D_NCOUNTERS)) return rc;
+  CK(cudaMemsetAsync(Q.block_tally, 0, (size_t)D.n_tally_rows * R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
+  CK(cudaMemsetAsync(Q.alive, 0, P, D.stream));
+  CK(cudaMallocHost(&D.h_flag, sizeof(uint32_t)));
+  D.steps_per_batch = std::max(1, env_int("R3D_STEPS_PER_BATCH", 16));
+
   CK(cudaStreamSynchronize(D.stream));
   CK(cudaGetLastError());
   return 0;
 }
 
-void destroy_device(DevState &D) {
-  if (D.device < 0) return;
-  cudaSetDevice(D.device);
-  if (D.stream) cudaStreamSynchronize(D.stream);
-  for (auto &ev : D.timing) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-  for (void *p : D.allocs) cudaFree(p);
-  if (D.stream) cudaStreamDestroy(D.stream);
-  D.allocs.clear(); D.timing.clear(); D.stream = nullptr;
+// The step loop of one job on one device (called on the device's worker thread).
+int run_job(DevState &D, const JobReq &jr) {
+  CK(cudaSetDevice(D.device));
+  cudaEvent_t ev0, ev1;
+  CK(cudaEventCreate(&ev0));
+  CK(cudaEventCreate(&ev1));
+  CK(cudaEventRecord(ev0, D.stream));
+  if (jr.n) {
+    const bool trace = jr.finals != nullptr;
+    Pool Q = D.Q;
+    // no more slots than phonons (a small job keeps its whole population in flight at once)
+    const unsigned long long want = (jr.n + 255ull) / 256ull * 256ull;
+    if (want < Q.n_slots) Q.n_slots = (uint32_t)want;
+    Job J; J.first = jr.first; J.n = jr.n; J.seed = jr.seed; J.finals = jr.finals;
+    const uint32_t n_tiles = Q.n_slots / R3D_A_THREADS;
+    const int gridA = (int)std::min<uint32_t>((uint32_t)D.gridA, n_tiles);
+    const int gridB = (int)std::min<uint32_t>((uint32_t)D.gridB, (Q.n_slots + R3D_B_THREADS - 1) / R3D_B_THREADS);
+    const int gridC = (int)std::min<uint32_t>((uint32_t)D.gridC, (Q.n_slots + R3D_C_THREADS - 1) / R3D_C_THREADS);
+    advance_fn fa = pick_advance(D.cell_kind, trace);
+    draw_fn fb = pick_draw(trace);
+    interface_fn fc = pick_interface(D.cell_kind, trace);
+    CK(cudaMemsetAsync(D.M.next_phonon, 0, sizeof(unsigned long long), D.stream));
+    CK(cudaMemsetAsync(Q.alive, 0, Q.n_slots, D.stream));
+    for (;;) {
+      for (int k = 0; k < D.steps_per_batch; k++) {
+        CK(cudaMemsetAsync(Q.q_count, 0, 4 * sizeof(uint32_t), D.stream));
+        fa<<<gridA, R3D_A_THREADS, D.smemA, D.stream>>>(D.M, Q, J, D.cells_in_smem);
+        fb<<<gridB, R3D_B_THREADS, 0, D.stream>>>(D.M, Q, (uint32_t)D.gridA);
+        fc<<<gridC, R3D_C_THREADS, D.smemC, D.stream>>>(D.M, Q, J, D.cells_in_smem, (uint32_t)(D.gridA + D.gridB));
+        D.launches += 3; D.steps++;
+      }
+      CK(cudaMemcpyAsync(D.h_flag, Q.q_count + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, D.stream));
+      CK(cudaStreamSynchronize(D.stream));
+      CK(cudaGetLastError());
+      if (!*D.h_flag) break;               // the last advance step found no live phonon and had none to start
+    }
+  }
+  reduce_tally_kernel<<<R3D_NCOUNTERS, 256, 0, D.stream>>>(D.Q.block_tally, D.n_tally_rows, D.M.counters);
+  D.launches += 1;
+  CK(cudaEventRecord(ev1, D.stream));
+  CK(cudaStreamSynchronize(D.stream));
+  CK(cudaGetLastError());
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ev0, ev1));
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+  { std::lock_guard<std::mutex> lk(D.mu); D.seconds += ms * 1e-3; }
+  return 0;
 }
 
-int launch(r3d_handle *h, DevState &D, unsigned long long first, unsigned long long n, unsigned long long seed, r3d_phonon_final *finals) {
-  CK(cudaSetDevice(D.device));
-  cudaEvent_t a, b;
-  CK(cudaEventCreate(&a));
-  CK(cudaEventCreate(&b));
-  D.timing.push_back({a, b});
-  CK(cudaMemsetAsync(D.M.next_phonon, 0, sizeof(unsigned long long), D.stream));
-  CK(cudaEventRecord(a, D.stream));
-  if (n) {
-    // no more CTAs than there is work for (one warp drains R3D_CHUNK phonons at a time)
-    unsigned long long want = (n + R3D_THREADS - 1) / R3D_THREADS;
-    int grid = (int)std::min<unsigned long long>((unsigned long long)D.grid, std::max<unsigned long long>(want, 1));
-    pick_kernel(h->cell_kind, finals != nullptr)<<<grid, R3D_THREADS, D.smem, D.stream>>>(D.M, first, n, seed, D.cells_in_smem, finals);
-    h->launches++;
+void worker_main(DevState *D) {
+  for (;;) {
+    JobReq jr;
+    {
+      std::unique_lock<std::mutex> lk(D->mu);
+      D->cv.wait(lk, [&] { return D->stop || !D->jobs.empty(); });
+      if (D->jobs.empty()) return;          // stop requested and nothing left to do
+      jr = D->jobs.front();
+      D->jobs.pop_front();
+      D->busy = true;
+    }
+    int rc = 0;
+    {
+      bool skip;
+      { std::lock_guard<std::mutex> lk(D->mu); skip = D->err_code != 0; }
+      if (!skip) rc = run_job(*D, jr);
+    }
+    {
+      std::lock_guard<std::mutex> lk(D->mu);
+      if (rc && !D->err_code) { D->err_code = rc; D->err = g_err; }
+      D->busy = false;
+    }
+    D->cv.notify_all();
   }
-  CK(cudaEventRecord(b, D.stream));
-  CK(cudaGetLastError());
+}
+
+void enqueue(DevState &D, const JobReq &jr) {
+  { std::lock_guard<std::mutex> lk(D.mu); D.jobs.push_back(jr); }
+  D.cv.notify_all();
+}
+
+// wait until the device has drained its job queue; returns its first error, if any
+int drain(DevState &D) {
+  std::unique_lock<std::mutex> lk(D.mu);
+  D.cv.wait(lk, [&] { return D.jobs.empty() && !D.busy; });
+  if (D.err_code) {
+    int rc = D.err_code;
+    g_err = D.err;
+    D.err_code = 0; D.err.clear();
+    return rc;
+  }
   return 0;
+}
+
+void destroy_device(DevState *D) {
+  if (!D) return;
+  if (D->worker.joinable()) {
+    { std::lock_guard<std::mutex> lk(D->mu); D->stop = true; }
+    D->cv.notify_all();
+    D->worker.join();
+  }
+  if (D->device >= 0) {
+    cudaSetDevice(D->device);
+    if (D->stream) cudaStreamSynchronize(D->stream);
+    for (void *p : D->allocs) cudaFree(p);
+    if (D->h_flag) cudaFreeHost(D->h_flag);
+    if (D->stream) cudaStreamDestroy(D->stream);
+  }
+  delete D;
 }
 
 }  // namespace
@@ -658,16 +524,16 @@ int r3d_create(const r3d_model_desc *desc, const int *devices, int n_dev, r3d_ha
   if (e != cudaSuccess || count == 0)
     return fail(R3D_ENODEV, std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
   if (n_dev <= 0) return fail(R3D_EINVAL, "n_dev must be >= 1");
-  int guide_bits = -1;
-  if (const char *s = getenv("R3D_GUIDE_BITS")) guide_bits = atoi(s);
   r3d_handle *h = new r3d_handle();
   h->cell_kind = desc->cell_kind; h->n_seis = desc->n_seis; h->n_bins = desc->n_bins;
-  h->devs.resize(n_dev);
   for (int i = 0; i < n_dev; i++) {
     int dev = devices ? devices[i] : i;
     if (dev < 0 || dev >= count) { r3d_destroy(h); return fail(R3D_ENODEV, "device index out of range"); }
-    h->devs[i].device = dev;
-    if (int rc = build_device(h->devs[i], desc, guide_bits)) { std::string keep = g_err; r3d_destroy(h); g_err = keep; return rc; }
+    DevState *D = new DevState();
+    h->devs.push_back(D);
+    D->device = dev;
+    if (int rc = build_device(*D, desc)) { std::string keep = g_err; r3d_destroy(h); g_err = keep; return rc; }
+    D->worker = std::thread(worker_main, D);
   }
   *out = h;
   return 0;
@@ -675,7 +541,7 @@ int r3d_create(const r3d_model_desc *desc, const int *devices, int n_dev, r3d_ha
 
 void r3d_destroy(r3d_handle *h) {
   if (!h) return;
-  for (auto &D : h->devs) destroy_device(D);
+  for (DevState *D : h->devs) destroy_device(D);
   delete h;
 }
 
@@ -685,7 +551,8 @@ int r3d_run(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons, uint64_t s
   for (uint64_t g = 0; g < G; g++) {      // contiguous index ranges
     uint64_t lo = n_phonons / G * g + (n_phonons % G) * g / G;
     uint64_t hi = n_phonons / G * (g + 1) + (n_phonons % G) * (g + 1) / G;
-    if (int rc = launch(h, h->devs[g], first_phonon + lo, hi - lo, seed, nullptr)) return rc;
+    JobReq jr; jr.first = first_phonon + lo; jr.n = hi - lo; jr.seed = seed; jr.finals = nullptr;
+    enqueue(*h->devs[g], jr);
   }
   return 0;
 }
@@ -693,21 +560,16 @@ int r3d_run(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons, uint64_t s
 int r3d_sync(r3d_handle *h, double *device_seconds) {
   if (!h) return fail(R3D_EINVAL, "null handle");
   double worst = 0;
-  for (auto &D : h->devs) {
-    CK(cudaSetDevice(D.device));
-    CK(cudaStreamSynchronize(D.stream));
-    double sum = 0;
-    for (auto &ev : D.timing) {
-      float ms = 0;
-      CK(cudaEventElapsedTime(&ms, ev.first, ev.second));
-      sum += ms * 1e-3;
-      cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
-    }
-    D.timing.clear();
-    worst = std::max(worst, sum);
+  int rc = 0;
+  for (DevState *D : h->devs) {
+    int r = drain(*D);
+    if (r && !rc) rc = r;
+    std::lock_guard<std::mutex> lk(D->mu);
+    worst = std::max(worst, D->seconds);
+    D->seconds = 0;
   }
   if (device_seconds) *device_seconds = worst;
-  return 0;
+  return rc;
 }
 
 int r3d_fetch(r3d_handle *h, double *energies, uint64_t *counts, uint64_t *counters, uint32_t *diag) {
@@ -719,7 +581,8 @@ int r3d_fetch(r3d_handle *h, double *energies, uint64_t *counts, uint64_t *count
   if (energies) memset(energies, 0, nb * R3D_BIN_NF64 * sizeof(double));
   if (counts) memset(counts, 0, nb * R3D_BIN_NCNT * sizeof(uint64_t));
   for (size_t g = 0; g < h->devs.size(); g++) {
-    DevState &D = h->devs[g];
+    DevState &D = *h->devs[g];
+    if (int rc = drain(D)) return rc;
     CK(cudaSetDevice(D.device));
     CK(cudaStreamSynchronize(D.stream));
     if (energies && nb) {
@@ -749,46 +612,54 @@ int r3d_fetch(r3d_handle *h, double *energies, uint64_t *counts, uint64_t *count
 int r3d_reset(r3d_handle *h) {
   if (!h) return fail(R3D_EINVAL, "null handle");
   const size_t nb = std::max<size_t>((size_t)h->n_seis * h->n_bins, 1);
-  for (auto &D : h->devs) {
+  for (DevState *Dp : h->devs) {
+    DevState &D = *Dp;
+    if (int rc = drain(D)) return rc;
     CK(cudaSetDevice(D.device));
     CK(cudaMemsetAsync(D.M.energies, 0, nb * R3D_BIN_NF64 * sizeof(double), D.stream));
     CK(cudaMemsetAsync(D.M.counts, 0, nb * R3D_BIN_NCNT * sizeof(unsigned long long), D.stream));
     CK(cudaMemsetAsync(D.M.counters, 0, R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
+    CK(cudaMemsetAsync(D.Q.block_tally, 0, (size_t)D.n_tally_rows * R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
+    CK(cudaStreamSynchronize(D.stream));
   }
   return 0;
 }
 
 int r3d_device_accumulators(r3d_handle *h, int dev_slot, void **energies, void **counts, void **counters) {
   if (!h || dev_slot < 0 || dev_slot >= (int)h->devs.size()) return fail(R3D_EINVAL, "bad handle or device slot");
-  if (energies) *energies = h->devs[dev_slot].M.energies;
-  if (counts) *counts = h->devs[dev_slot].M.counts;
-  if (counters) *counters = h->devs[dev_slot].M.counters;
+  if (energies) *energies = h->devs[dev_slot]->M.energies;
+  if (counts) *counts = h->devs[dev_slot]->M.counts;
+  if (counters) *counters = h->devs[dev_slot]->M.counters;
   return 0;
 }
 
 int r3d_stream(r3d_handle *h, int dev_slot, void **stream) {
   if (!h || dev_slot < 0 || dev_slot >= (int)h->devs.size() || !stream) return fail(R3D_EINVAL, "bad handle or device slot");
-  *stream = h->devs[dev_slot].stream;
+  *stream = h->devs[dev_slot]->stream;
   return 0;
 }
 
 int r3d_launch_count(r3d_handle *h, uint64_t *n) {
   if (!h || !n) return fail(R3D_EINVAL, "null argument");
-  *n = h->launches;
+  uint64_t tot = 0;
+  for (DevState *D : h->devs) { if (int rc = drain(*D)) return rc; tot += D->launches; }
+  *n = tot;
   return 0;
 }
 
 int r3d_trace(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons, uint64_t seed, r3d_phonon_final *out) {
   if (!h || !out) return fail(R3D_EINVAL, "null argument");
   if (!n_phonons) return 0;
-  DevState &D = h->devs[0];
+  DevState &D = *h->devs[0];
+  if (int rc = drain(D)) return rc;
   CK(cudaSetDevice(D.device));
   r3d_phonon_final *dfin = nullptr;
   CK(cudaMalloc(&dfin, n_phonons * sizeof(r3d_phonon_final)));
-  int rc = launch(h, D, first_phonon, n_phonons, seed, dfin);
+  JobReq jr; jr.first = first_phonon; jr.n = n_phonons; jr.seed = seed; jr.finals = dfin;
+  enqueue(D, jr);
+  int rc = drain(D);
   cudaError_t e = cudaSuccess;
-  if (!rc) e = cudaStreamSynchronize(D.stream);
-  if (!rc && e == cudaSuccess) e = cudaMemcpy(out, dfin, n_phonons * sizeof(r3d_phonon_final), cudaMemcpyDeviceToHost);
+  if (!rc) e = cudaMemcpy(out, dfin, n_phonons * sizeof(r3d_phonon_final), cudaMemcpyDeviceToHost);
   cudaFree(dfin);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(R3D_ECUDA, std::string("r3d_trace: ") + cudaGetErrorString(e));
@@ -819,7 +690,8 @@ int need_device() {
 }
 int path_hook(r3d_handle *h, const double *in, uint32_t n, double *out, int advance_mode) {
   if (!h || !in || !out) return fail(R3D_EINVAL, "null argument");
-  DevState &D = h->devs[0];
+  DevState &D = *h->devs[0];
+  if (int rc = drain(D)) return rc;
   CK(cudaSetDevice(D.device));
   Scratch S;
   double *din, *dout;
