@@ -222,6 +222,14 @@ int r3d_stream(r3d_handle *h, int dev_slot, void **stream);
 /* Number of kernels this handle has launched so far. */
 int r3d_launch_count(r3d_handle *h, uint64_t *n);
 
+/* Per-kernel timing for the roofline report.  While profiling is on, every kernel launch of the step loop
+ * is bracketed by CUDA events on the launching stream (this slows the loop down a little, so timed
+ * throughput runs leave it off).  r3d_kernel_times returns, for device slot 0, the accumulated device
+ * seconds and launch counts of [0] the advance kernel, [1] the draw kernel, [2] the interface kernel, and
+ * the number of units each processed: [0] live phonons advanced, [1] table draws, [2] face events. */
+int r3d_set_profiling(r3d_handle *h, int on);
+int r3d_kernel_times(r3d_handle *h, double seconds[3], uint64_t launches[3], uint64_t units[3]);
+
 /* Parity hook: trace phonons [first, first+n) on device slot 0 WITHOUT touching
  * the accumulators' semantics (bins are still accumulated) and write each
  * phonon's end state to out[n] (host memory). */
@@ -236,6 +244,8 @@ int r3d_trace(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons,
  * 31-bit draws k[n]: out[i] = smallest j with cdf[n_cdf-1]*(k/RAND_MAX) <= cdf[j]. */
 int r3d_test_cdf_search(const double *cdf, uint32_t n_cdf, const uint32_t *k,
                         uint32_t n, uint32_t *out, int use_guide_table);
+/* use_guide_table: 0 = the reference's plain bisection, 1 = exact guide table of the default size,
+ * n > 1 = exact guide table with 2^n buckets. */
 
 /* GetPathToBoundary (media.cpp:236,518,668) for phonons in given cells:
  * in[i] = {cell, type, x,y,z, theta, phi} as 7 doubles;

@@ -1,0 +1,139 @@
+// r3d_run_simulation_gpu.cpp -- the reference-side binding of the GPU propagate path.
+//
+// This file DEFINES Model::RunSimulation() for the reference program.  It is linked with the reference's
+// own, unmodified translation units (compiled from the reference checkout where it lies; model.cpp is
+// compiled with -DRunSimulation=RunSimulation_reference_cpu so that its CPU loop keeps existing under
+// another name) and with libr3dgpu.so.  Everything before the loop -- command line, user_*_inc.cpp model
+// plugins, grid, cells, scatterer tables, source, seismometers -- and everything after it -- the stdout
+// summary, seis_traces_asc.dat and seis_NNN.octv writers (dataout.cpp:249-406, 623-694) -- is the
+// reference's own code.  Only the body of the loop at model.cpp:611-625 is replaced:
+//
+//     for (i < mNumPhonons) { Phonon P = mpEventSource->GenerateEventPhonon(); P.Propagate(); }
+//  ==>
+//     flatten model -> r3d_create -> r3d_run (10 slices, for the progress lines) -> r3d_fetch
+//     -> write bins / counters back into Seismometer / DataReporter objects
+//
+// Environment (all optional):
+//   R3D_GPU_DEVICES=0,1,...   CUDA devices to shard the phonon index range over   (default: 0)
+//   R3D_GPU_SEED=<u64>        Philox seed (default: time(NULL), like the reference's srand(time(NULL)))
+//   R3D_GPU_NUM_PHONONS=<u64> 64-bit phonon count, overrides --num-phonons (the reference's is an int)
+//   R3D_GPU_DUMP_MODEL=<path> also write the flattened model (include/r3d_modelfile.h)
+//   R3D_GPU_DUMP_ONLY=1       ... and return without simulating
+#include <iostream>
+#include <fstream>
+#include <sstream>
+#include <vector>
+#include <map>
+#include <string>
+#include <cstdlib>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <complex>
+#include <stdexcept>
+#include <ctime>
+#include <climits>
+
+#define private public
+#define protected public
+#include "model.hpp"
+#include "media.hpp"
+#include "phonons.hpp"
+#include "scatterers.hpp"
+#include "events.hpp"
+#include "ecs.hpp"
+#include "dataout.hpp"
+#undef private
+#undef protected
+
+#include "r3d_modelfile.h"
+#include "r3d_flatten.hpp"
+
+namespace {
+void r3d_check(int rc, const char * what) {
+  if (rc != 0)   // same convention as the rest of the program: user-facing failure -> Runtime (typedefs.hpp:123)
+    throw Runtime(std::string("GPU propagate path: ") + what + ": " + r3d_last_error());
+}
+}
+
+void Model::RunSimulation() {
+
+  FlatModel F;
+  Flatten(*this, F);
+
+  if (const char * path = getenv("R3D_GPU_DUMP_MODEL")) {
+    if (r3d_modelfile_write(path, &F.d) != 0) throw Runtime(std::string("cannot write model file ") + path);
+    std::cerr << "r3d-gpu: wrote flattened model to " << path << "\n";
+    if (getenv("R3D_GPU_DUMP_ONLY")) return;
+  }
+
+  std::vector<int> devices;
+  if (const char * s = getenv("R3D_GPU_DEVICES")) {
+    std::stringstream ss(s);
+    std::string tok;
+    while (std::getline(ss, tok, ',')) if (!tok.empty()) devices.push_back(atoi(tok.c_str()));
+  }
+  if (devices.empty()) devices.push_back(0);
+  uint64_t seed = (uint64_t)time(NULL);
+  if (const char * s = getenv("R3D_GPU_SEED")) seed = strtoull(s, 0, 0);
+  uint64_t nph = (mNumPhonons > 0) ? (uint64_t)mNumPhonons : 0;
+  if (const char * s = getenv("R3D_GPU_NUM_PHONONS")) nph = strtoull(s, 0, 0);
+
+  r3d_handle * h = 0;
+  r3d_check(r3d_create(&F.d, devices.data(), (int)devices.size(), &h), "r3d_create");
+
+  std::cout << "@@ __BEGINNING_SIMULATION__" << std::endl << std::flush;
+
+  // ten slices so that the progress lines of model.cpp:616-628 keep appearing
+  double device_seconds = 0;
+  for (int slice = 0; slice < 10; slice++) {
+    uint64_t lo = nph / 10 * slice + (nph % 10) * slice / 10;
+    uint64_t hi = nph / 10 * (slice + 1) + (nph % 10) * (slice + 1) / 10;
+    std::cerr << slice * 10 << "% of " << nph << " have been cast.\n";
+    int rc = r3d_run(h, lo, hi - lo, seed);
+    double t = 0;
+    if (rc == 0) rc = r3d_sync(h, &t);
+    if (rc != 0) { std::string msg = r3d_last_error(); r3d_destroy(h); throw Runtime("GPU propagate path: " + msg); }
+    device_seconds += t;
+  }
+  std::cerr << "100% of " << nph << " have been cast.\n";
+  std::cout << "@@ __SIMULATION_COMPLETE__" << std::endl;
+
+  // bins and counters back into the reference's own objects
+  const size_t ns = dataout.mSeismometers.size(), nb = Seismometer::cmNumBins;
+  std::vector<double> e(ns * nb * R3D_BIN_NF64 + 1);
+  std::vector<uint64_t> c(ns * nb * R3D_BIN_NCNT + 1), k(R3D_NCOUNTERS);
+  uint32_t diag = 0;
+  int rc = r3d_fetch(h, e.data(), c.data(), k.data(), &diag);
+  if (rc != 0) { std::string msg = r3d_last_error(); r3d_destroy(h); throw Runtime("GPU propagate path: " + msg); }
+  r3d_destroy(h);
+  bool clipped = false;
+  for (size_t s = 0; s < ns; s++) {
+    Seismometer & S = *dataout.mSeismometers[s];
+    for (size_t b = 0; b < nb; b++) {
+      const double * eb = &e[(s * nb + b) * R3D_BIN_NF64];
+      const uint64_t * cb = &c[(s * nb + b) * R3D_BIN_NCNT];
+      S.mTimeBins[b].mEnergyAxes[0] += eb[0];
+      S.mTimeBins[b].mEnergyAxes[1] += eb[1];
+      S.mTimeBins[b].mEnergyAxes[2] += eb[2];
+      S.mTimeBins[b].mEnergyByType[RAY_P] += eb[3];
+      S.mTimeBins[b].mEnergyByType[RAY_S] += eb[4];
+      for (int t = 0; t < 2; t++) {           // the reference's counts are 32-bit (dataout.hpp:77-93)
+        uint64_t v = (uint64_t)S.mTimeBins[b].mCountByType[t] + cb[t];
+        if (v > UINT_MAX) { v = UINT_MAX; clipped = true; }
+        S.mTimeBins[b].mCountByType[t] = (unsigned)v;
+      }
+    }
+  }
+  if (clipped) std::cerr << "r3d-gpu: WARNING: a bin count exceeded 2^32-1 and was clipped in the output files.\n";
+  dataout.mNumLost += k[R3D_CNT_LOST];
+  dataout.mNumTimeout += k[R3D_CNT_TIMEOUT];
+  dataout.mNumInvalid += k[R3D_CNT_INVALID];
+  dataout.mDiagInvalid |= diag;
+
+  std::cerr << "r3d-gpu: " << nph << " phonons on " << devices.size() << " device(s) in " << device_seconds
+            << " s of device time (" << (device_seconds > 0 ? nph / device_seconds : 0) << " phonons/s), seed " << seed << "\n";
+
+  dataout.OutputPostSimSummary();
+
+}

@@ -173,6 +173,12 @@ struct DevState {
   std::string err;
   double seconds = 0;                      // device time of the jobs finished since the last r3d_sync
   unsigned long long launches = 0, steps = 0;
+  // optional per-kernel timing (r3d_set_profiling)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;    // 4 per step of a batch
+  uint32_t *h_qcounts = nullptr;           // pinned: [steps_per_batch][4] copies of q_count
+  double k_seconds[3] = {0, 0, 0};
+  unsigned long long k_launches[3] = {0, 0, 0}, k_units[3] = {0, 0, 0};
 };
 
 }  // namespace
@@ -418,17 +424,41 @@ int run_job(DevState &D, const JobReq &jr) {
     interface_fn fc = pick_interface(D.cell_kind, trace);
     CK(cudaMemsetAsync(D.M.next_phonon, 0, sizeof(unsigned long long), D.stream));
     CK(cudaMemsetAsync(Q.alive, 0, Q.n_slots, D.stream));
+    const bool prof = D.profiling;
+    if (prof && D.prof_events.empty()) {
+      D.prof_events.resize((size_t)4 * D.steps_per_batch);
+      for (auto &ev : D.prof_events) CK(cudaEventCreate(&ev));
+      CK(cudaMallocHost(&D.h_qcounts, (size_t)4 * D.steps_per_batch * sizeof(uint32_t)));
+    }
     for (;;) {
       for (int k = 0; k < D.steps_per_batch; k++) {
         CK(cudaMemsetAsync(Q.q_count, 0, 4 * sizeof(uint32_t), D.stream));
+        if (prof) CK(cudaEventRecord(D.prof_events[4 * k + 0], D.stream));
         fa<<<gridA, R3D_A_THREADS, D.smemA, D.stream>>>(D.M, Q, J, D.cells_in_smem);
+        if (prof) CK(cudaEventRecord(D.prof_events[4 * k + 1], D.stream));
         fb<<<gridB, R3D_B_THREADS, 0, D.stream>>>(D.M, Q, (uint32_t)D.gridA);
+        if (prof) CK(cudaEventRecord(D.prof_events[4 * k + 2], D.stream));
         fc<<<gridC, R3D_C_THREADS, D.smemC, D.stream>>>(D.M, Q, J, D.cells_in_smem, (uint32_t)(D.gridA + D.gridB));
+        if (prof) {
+          CK(cudaEventRecord(D.prof_events[4 * k + 3], D.stream));
+          CK(cudaMemcpyAsync(D.h_qcounts + 4 * k, Q.q_count, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, D.stream));
+        }
         D.launches += 3; D.steps++;
       }
       CK(cudaMemcpyAsync(D.h_flag, Q.q_count + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, D.stream));
       CK(cudaStreamSynchronize(D.stream));
       CK(cudaGetLastError());
+      if (prof) {
+        std::lock_guard<std::mutex> lk(D.mu);
+        for (int k = 0; k < D.steps_per_batch; k++)
+          for (int j = 0; j < 3; j++) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, D.prof_events[4 * k + j], D.prof_events[4 * k + j + 1]));
+            D.k_seconds[j] += ms * 1e-3;
+            D.k_launches[j] += 1;
+            D.k_units[j] += (j == 0) ? 0 : D.h_qcounts[4 * k + (j - 1)];
+          }
+      }
       if (!*D.h_flag) break;               // the last advance step found no live phonon and had none to start
     }
   }
@@ -500,6 +530,8 @@ void destroy_device(DevState *D) {
     if (D->stream) cudaStreamSynchronize(D->stream);
     for (void *p : D->allocs) cudaFree(p);
     if (D->h_flag) cudaFreeHost(D->h_flag);
+    if (D->h_qcounts) cudaFreeHost(D->h_qcounts);
+    for (auto &ev : D->prof_events) cudaEventDestroy(ev);
     if (D->stream) cudaStreamDestroy(D->stream);
   }
   delete D;
@@ -644,6 +676,30 @@ int r3d_launch_count(r3d_handle *h, uint64_t *n) {
   uint64_t tot = 0;
   for (DevState *D : h->devs) { if (int rc = drain(*D)) return rc; tot += D->launches; }
   *n = tot;
+  return 0;
+}
+
+int r3d_set_profiling(r3d_handle *h, int on) {
+  if (!h) return fail(R3D_EINVAL, "null handle");
+  for (DevState *D : h->devs) {
+    if (int rc = drain(*D)) return rc;
+    std::lock_guard<std::mutex> lk(D->mu);
+    D->profiling = on != 0;
+    for (int j = 0; j < 3; j++) { D->k_seconds[j] = 0; D->k_launches[j] = 0; D->k_units[j] = 0; }
+  }
+  return 0;
+}
+
+int r3d_kernel_times(r3d_handle *h, double seconds[3], uint64_t launches[3], uint64_t units[3]) {
+  if (!h || !seconds || !launches || !units) return fail(R3D_EINVAL, "null argument");
+  DevState &D = *h->devs[0];
+  if (int rc = drain(D)) return rc;
+  unsigned long long k[R3D_NCOUNTERS];
+  CK(cudaSetDevice(D.device));
+  CK(cudaMemcpy(k, D.M.counters, sizeof k, cudaMemcpyDeviceToHost));
+  std::lock_guard<std::mutex> lk(D.mu);
+  for (int j = 0; j < 3; j++) { seconds[j] = D.k_seconds[j]; launches[j] = D.k_launches[j]; units[j] = D.k_units[j]; }
+  units[0] = k[R3D_CNT_EVENTS];            // live phonons advanced == loop events tallied by the advance kernel
   return 0;
 }
 

@@ -21,7 +21,7 @@ _lib = None
 
 EXPORTS = [
     "r3d_create", "r3d_run", "r3d_sync", "r3d_fetch", "r3d_reset", "r3d_device_accumulators", "r3d_stream",
-    "r3d_launch_count", "r3d_trace", "r3d_test_cdf_search", "r3d_test_path_to_boundary", "r3d_test_advance",
+    "r3d_launch_count", "r3d_trace", "r3d_set_profiling", "r3d_kernel_times", "r3d_test_cdf_search", "r3d_test_path_to_boundary", "r3d_test_advance",
     "r3d_test_transform", "r3d_test_rtcoef", "r3d_test_catch", "r3d_destroy", "r3d_last_error", "r3d_abi_version",
 ]
 
@@ -55,6 +55,8 @@ def load_library(path=None):
     L.r3d_stream.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.r3d_launch_count.argtypes = [vp, pu64]
     L.r3d_trace.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
+    L.r3d_set_profiling.argtypes = [vp, C.c_int]
+    L.r3d_kernel_times.argtypes = [vp, pd, pu64, pu64]
     L.r3d_test_cdf_search.argtypes = [pd, C.c_uint32, pu32, C.c_uint32, pu32, C.c_int]
     L.r3d_test_path_to_boundary.argtypes = [vp, pd, C.c_uint32, pd]
     L.r3d_test_advance.argtypes = [vp, pd, C.c_uint32, pd]
@@ -155,6 +157,18 @@ class Engine:
         n = C.c_uint64()
         _ck(self._L, self._L.r3d_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def set_profiling(self, on=True):
+        """Bracket every kernel of the step loop with CUDA events (resets the per-kernel totals)."""
+        _ck(self._L, self._L.r3d_set_profiling(self._h, 1 if on else 0))
+
+    def kernel_times(self):
+        """{'advance'|'draw'|'interface': (device seconds, launches, units processed)} since set_profiling()."""
+        t = np.zeros(3)
+        n = np.zeros(3, dtype=np.uint64)
+        u = np.zeros(3, dtype=np.uint64)
+        _ck(self._L, self._L.r3d_kernel_times(self._h, _pd(t), abi.as_ptr(n, C.c_uint64), abi.as_ptr(u, C.c_uint64)))
+        return {name: (float(t[i]), int(n[i]), int(u[i])) for i, name in enumerate(("advance", "draw", "interface"))}
 
     def stream(self, slot=0):
         s = C.c_void_p()

@@ -3,8 +3,8 @@
 Assembled exactly as the reference's scripts/do-fundamentals.sh:396-419 does from the
 variables each do-script sets (do-halfspace.sh, do-halfspace-nearsrc50.sh,
 do-crustpinch.sh, do-lopnor.sh, do-spherical.sh), with only --num-phonons,
---toa-degree and --output-dir left open.  Used by the golden-fixture generator and
-by the tests that drive oracle/_ref.
+--toa-degree and --output-dir left open.  Used by the golden-fixture generator,
+by the tests, and by bench.py / the integration binary to build the model of a workload.
 """
 
 _HALFSPACE_ARGS = "0.8,0.01,1.0,0.5,1000,0.8,0.01,1.0,0.5,1000,6.40,3.63,2.83,-60,6.40,3.63,2.83,-400"

@@ -9,7 +9,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-import ref_configs  # noqa: E402
+from radiative3d_b200 import workloads as ref_configs  # noqa: E402
 from radiative3d_b200 import abi, engine  # noqa: E402
 from radiative3d_b200.model import FlatModel  # noqa: E402
 

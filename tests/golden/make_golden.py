@@ -27,7 +27,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-import ref_configs  # noqa: E402
+from radiative3d_b200 import workloads as ref_configs  # noqa: E402
 from radiative3d_b200 import abi  # noqa: E402
 from radiative3d_b200.model import FlatModel, _ARRAYS  # noqa: E402
 from oracle_binding import load_bins  # noqa: E402
