@@ -258,6 +258,67 @@ int validate(const r3d_model_desc *d) {
   return 0;
 }
 
+int env_int(const char *name, int dflt);
+
+// Uniform grid over the seismometers' bounding spheres: cell -> list of seismometers whose (slightly inflated) sphere
+// box overlaps it.  A phonon looks up the cell of its position and runs the exact CatchPhonon test only on that list.
+int build_seis_grid(DevState &D, const r3d_model_desc *d) {
+  DevModel &M = D.M;
+  const uint32_t ns = d->n_seis;
+  std::vector<uint32_t> start(2, 0), items;
+  for (int a = 0; a < 3; a++) { M.grid_min[a] = 0; M.grid_inv_h[a] = 0; M.grid_dim[a] = 1; }
+  if (ns) {
+    std::vector<double> rad(ns);
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (uint32_t i = 0; i < ns; i++) {
+      const double *s = d->seis + (size_t)i * R3D_SEIS_NPARAM;
+      double r = std::max(s[14], s[15]);
+      rad[i] = r * (1.0 + 1e-6) + 1e-9 * (1.0 + fabs(s[0]) + fabs(s[1]) + fabs(s[2]));     // covers r_out with margin
+      for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], s[a] - rad[i]); hi[a] = std::max(hi[a], s[a] + rad[i]); }
+    }
+    std::vector<double> sorted(rad);
+    std::sort(sorted.begin(), sorted.end());
+    double h = 2.0 * sorted[ns / 2];                       // a typical sphere spans about one cell
+    if (!(h > 0)) h = 1.0;
+    const int max_dim = std::max(1, env_int("R3D_GRID_MAX_DIM", 128));
+    for (int a = 0; a < 3; a++) {
+      double ext = hi[a] - lo[a];
+      double ha = std::max(h, ext / max_dim);
+      uint32_t dim = (uint32_t)std::max(1.0, ceil(ext / ha) + 1.0);
+      M.grid_min[a] = lo[a]; M.grid_inv_h[a] = 1.0 / ha; M.grid_dim[a] = dim;
+    }
+    auto cell_of = [&](double x, int a) {                  // same expression as grid_axis_cell() on the device
+      long c = (long)floor((x - M.grid_min[a]) * M.grid_inv_h[a]);
+      return (uint32_t)std::min<long>(std::max<long>(c, 0), (long)M.grid_dim[a] - 1);
+    };
+    const size_t ncell = (size_t)M.grid_dim[0] * M.grid_dim[1] * M.grid_dim[2];
+    start.assign(ncell + 1, 0);
+    for (int pass = 0; pass < 2; pass++) {
+      std::vector<uint32_t> fill;
+      if (pass == 1) {
+        for (size_t c = 0, run = 0; c <= ncell; c++) { uint32_t n = c < ncell ? start[c] : 0; start[c] = (uint32_t)run; run += n; }
+        items.assign(start[ncell], 0);
+        fill.assign(start.begin(), start.end() - 1);
+      }
+      for (uint32_t i = 0; i < ns; i++) {
+        const double *s = d->seis + (size_t)i * R3D_SEIS_NPARAM;
+        uint32_t c0[3], c1[3];
+        for (int a = 0; a < 3; a++) { c0[a] = cell_of(s[a] - rad[i], a); c1[a] = cell_of(s[a] + rad[i], a); }
+        for (uint32_t z = c0[2]; z <= c1[2]; z++)
+          for (uint32_t y = c0[1]; y <= c1[1]; y++)
+            for (uint32_t x = c0[0]; x <= c1[0]; x++) {
+              size_t c = ((size_t)z * M.grid_dim[1] + y) * M.grid_dim[0] + x;
+              if (pass == 0) start[c]++; else items[fill[c]++] = i;
+            }
+      }
+    }
+  }
+  if (int rc = dev_upload(D, &M.grid_start, start.data(), start.size())) return rc;
+  if (int rc = dev_upload(D, &M.grid_items, items.data(), items.size())) return rc;
+  CK(cudaStreamSynchronize(D.stream));                      // the host vectors go out of scope
+  return 0;
+}
+
 int env_int(const char *name, int dflt) {
   const char *s = getenv(name);
   return (s && *s) ? atoi(s) : dflt;
@@ -301,6 +362,7 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   if (int rc = dev_alloc(D, &sph, d->n_seis)) return rc;
   if (d->n_seis) seis_sphere_kernel<<<(d->n_seis + 127) / 128, 128, 0, D.stream>>>(M.seis, d->n_seis, sph);
   M.seis_sphere = sph;
+  if (int rc = build_seis_grid(D, d)) return rc;
 
   // guide tables: exact only for non-decreasing CDFs; otherwise fall back to the plain bisection
   int *bad = nullptr;

@@ -10,7 +10,8 @@
 //                                           distance to boundary; path-length draw; move; cheap hand-overs inline
 //   draw      (one thread per queued draw)  exact guide-table CDF search, take-off-angle fetch, then either
 //                                           source-phonon initialisation or Phonon::Transform
-//   interface (one warp per 32 queued hits) warp-cooperative seismometer scan, then R/T coefficients / ray bending
+//   interface (one thread per queued hit)   seismometer catch through a uniform-grid index, then R/T coefficients /
+//                                           ray bending
 // The price is HBM traffic for the state (~300 B per event), which is what a B200 has to spare on this workload.
 #pragma once
 #include "r3d_device.cuh"
@@ -382,7 +383,7 @@ R3D_DEV void refraction_bend(const DevModel &M, const double *cells, Phonon &p, 
 }
 
 template <class Cell, bool TRACE>
-__global__ void __launch_bounds__(R3D_C_THREADS)
+__global__ void __launch_bounds__(R3D_C_THREADS, 4)
 interface_kernel(const DevModel M, const Pool Q, const Job J, int cells_in_smem, uint32_t tally_row0) {
   extern __shared__ double4 smem_c4[];
   __shared__ unsigned long long tally_sm[R3D_C_THREADS / 32][R3D_NCOUNTERS];
@@ -397,7 +398,6 @@ interface_kernel(const DevModel M, const Pool Q, const Job J, int cells_in_smem,
   }
   __syncthreads();
   const double *cells = cells_in_smem ? scells : M.cell_params;
-  const unsigned lane = threadIdx.x & 31u;
 
   const uint32_t n_round = (n + 31u) & ~31u;                  // whole warps stay in the loop together
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
@@ -419,60 +419,35 @@ interface_kernel(const DevModel M, const Pool Q, const Job J, int cells_in_smem,
       other = __ldg(M.face_other + fi);
     }
 
-    // ---- collection: the warp scans the seismometers together, one collected phonon at a time -----------
-    unsigned cmask = __ballot_sync(R3D_FULL, have && (fl & R3D_FACE_COLLECT) && M.n_seis > 0);
+    // ---- collection (dataout.cpp:545-568): every seismometer is pass-through (dataout.cpp:50), so all that contain
+    // the point must bin it.  Candidates come from the uniform grid over the seismometers' bounding spheres. --------
     uint32_t my_catches = 0;
-    while (cmask) {
-      const int src = __ffs(cmask) - 1;
-      cmask &= cmask - 1;
-      const double bx = __shfl_sync(R3D_FULL, p.loc.x, src), by = __shfl_sync(R3D_FULL, p.loc.y, src), bz = __shfl_sync(R3D_FULL, p.loc.z, src);
-      uint32_t hits = 0;                                      // candidate seismometers of this lane, 1 bit per round
-      const uint32_t rounds = (M.n_seis + 31u) >> 5;
-      unsigned any = 0;
-      for (uint32_t r = 0; r < rounds; r++) {
-        const uint32_t k = r * 32u + lane;
-        bool hit = false;
-        if (k < M.n_seis) {
-          const double4 q = sph[k];
-          const double dx = q.x - bx, dy = q.y - by, dz = q.z - bz;
-          hit = !(dx * dx + dy * dy + dz * dz > q.w);
-        }
-        if (hit) hits |= 1u << (r & 31u);
-        any |= __ballot_sync(R3D_FULL, hit);
-        if ((r & 31u) == 31u || r + 1 == rounds) {
-          if (any) {
-            // exact test by the lanes that hold candidates; the phonon is broadcast from lane src
-            const double b_time = __shfl_sync(R3D_FULL, p.time, src), b_amp = __shfl_sync(R3D_FULL, p.amp, src);
-            const double b_th = __shfl_sync(R3D_FULL, p.th, src), b_ph = __shfl_sync(R3D_FULL, p.ph, src), b_pol = __shfl_sync(R3D_FULL, p.pol, src);
-            const int b_type = __shfl_sync(R3D_FULL, p.type, src);
-            const uint32_t b_cell = __shfl_sync(R3D_FULL, p.cell, src);
-            uint32_t got = 0;
-            if (hits) {
-              const v3 bloc = V(bx, by, bz);
-              const double vel = Cell::veloc(cells + (size_t)b_cell * M.cell_nparam, b_type, bloc);
-              const v3 dir = from_thph(b_th, b_ph);
-              const v3 dopm = dir_of_motion(b_type, b_th, b_ph, b_pol);
-              const uint32_t r0 = r & ~31u;
-              while (hits) {
-                const uint32_t rr = r0 + (__ffs(hits) - 1);
-                hits &= hits - 1;
-                const uint32_t k2 = rr * 32u + lane;
-                uint32_t bin; double e[4];
-                if (seis_catch(M.seis + (size_t)k2 * R3D_SEIS_NPARAM, M.bin_dt, M.n_bins, b_time, bloc, dir, dopm, b_type, b_amp, vel, bin, e)) {
-                  const size_t b = (size_t)k2 * M.n_bins + bin;
-                  atomicAdd(M.energies + b * 5 + 0, e[0]);
-                  atomicAdd(M.energies + b * 5 + 1, e[1]);
-                  atomicAdd(M.energies + b * 5 + 2, e[2]);
-                  atomicAdd(M.energies + b * 5 + 3 + b_type, e[3]);
-                  atomicAdd(M.counts + b * 2 + b_type, 1ull);
-                  got++;
-                }
-              }
-            }
-            for (int o = 16; o > 0; o >>= 1) got += __shfl_xor_sync(R3D_FULL, got, o);
-            if ((int)lane == src) my_catches += got;
+    if (have && (fl & R3D_FACE_COLLECT) && M.n_seis > 0) {
+      const int cx_ = grid_axis_cell(p.loc.x, M.grid_min[0], M.grid_inv_h[0]);
+      const int cy_ = grid_axis_cell(p.loc.y, M.grid_min[1], M.grid_inv_h[1]);
+      const int cz_ = grid_axis_cell(p.loc.z, M.grid_min[2], M.grid_inv_h[2]);
+      if (cx_ >= 0 && cy_ >= 0 && cz_ >= 0 && cx_ < (int)M.grid_dim[0] && cy_ < (int)M.grid_dim[1] && cz_ < (int)M.grid_dim[2]) {
+        const uint32_t cell = ((uint32_t)cz_ * M.grid_dim[1] + (uint32_t)cy_) * M.grid_dim[0] + (uint32_t)cx_;
+        const uint32_t i0 = __ldg(M.grid_start + cell), i1 = __ldg(M.grid_start + cell + 1);
+        for (uint32_t j = i0; j < i1; j++) {
+          const uint32_t k2 = __ldg(M.grid_items + j);
+          const double4 q = sph[k2];
+          const double dx = q.x - p.loc.x, dy = q.y - p.loc.y, dz = q.z - p.loc.z;
+          if (dx * dx + dy * dy + dz * dz > q.w) continue;       // cannot be within the gather radius
+          // rare from here on (a few per cent of the surface hits): the exact CatchPhonon test
+          const double vel = Cell::veloc(cells + (size_t)p.cell * M.cell_nparam, p.type, p.loc);
+          const v3 dir = from_thph(p.th, p.ph);
+          const v3 dopm = dir_of_motion(p.type, p.th, p.ph, p.pol);
+          uint32_t bin; double e[4];
+          if (seis_catch(M.seis + (size_t)k2 * R3D_SEIS_NPARAM, M.bin_dt, M.n_bins, p.time, p.loc, dir, dopm, p.type, p.amp, vel, bin, e)) {
+            const size_t b = (size_t)k2 * M.n_bins + bin;
+            atomicAdd(M.energies + b * 5 + 0, e[0]);
+            atomicAdd(M.energies + b * 5 + 1, e[1]);
+            atomicAdd(M.energies + b * 5 + 2, e[2]);
+            atomicAdd(M.energies + b * 5 + 3 + p.type, e[3]);
+            atomicAdd(M.counts + b * 2 + p.type, 1ull);
+            my_catches++;
           }
-          any = 0; hits = 0;
         }
       }
     }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Scratch: one warm-up launch + one measured launch of the propagate kernel, for ncu.
-usage: profile_target.py <config> <toa degree> <n phonons>   (model built by the oracle/_ref harness)"""
+usage: profile_target.py <config> <toa degree> <n phonons>   (model built by integration/_build/r3d_gpu_main)"""
 import os
 import subprocess
 import sys
@@ -14,11 +14,8 @@ from radiative3d_b200 import abi, engine  # noqa: E402
 from radiative3d_b200.model import FlatModel  # noqa: E402
 
 cfg, deg, n = sys.argv[1], int(sys.argv[2]), int(float(sys.argv[3]))
-with tempfile.TemporaryDirectory() as tmp:
-    env = dict(os.environ, R3D_HARNESS="dump", R3D_HARNESS_OUT=os.path.join(tmp, "m"))
-    subprocess.run([os.path.join(ROOT, "oracle/_ref/r3d_ref_harness")] + ref_configs.cmdline(cfg, 10, deg, tmp), cwd=tmp,
-                   env=env, check=True, capture_output=True)
-    m = FlatModel.load(os.path.join(tmp, "m"))
+from radiative3d_b200 import reference_host  # noqa: E402
+m = reference_host.build_model(cfg, deg)
 eng = engine.Engine(m)
 eng.run_simulation(n, seed=1)
 eng.sync()
