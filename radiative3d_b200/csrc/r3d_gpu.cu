@@ -39,13 +39,23 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
 // ---------------------------------------------------------------------------
 // model-preparation kernels
 // ---------------------------------------------------------------------------
-__global__ void pack_toa_kernel(const double *th, const double *ph, double2 *out, uint32_t n, double mn, double mx) {
+__global__ void pack_toa_kernel(const double *th, const double *ph, double4 *out, uint32_t n, double mn, double mx) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double t = th[i];
   if (t < mn) t = mn;                    // Phonon::nudge_if_singular (phonons.hpp:335-344), applied where the
   if (t > mx) t = mx;                    // reference constructs a Phonon from a TOA entry
-  out[i] = make_double2(t, ph[i]);
+  double st, ct, sp, cp;
+  sincos(t, &st, &ct);
+  sincos(ph[i], &sp, &cp);
+  out[i] = make_double4(st, ct, sp, cp);
+}
+__global__ void pack_spol_kernel(const double *spol, double2 *out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s_, c_;
+  sincos(spol[i], &s_, &c_);
+  out[i] = make_double2(c_, s_);
 }
 // guide[j] = lower_bound of r(k = min(j << shift, RAND_MAX)) for every table
 __global__ void build_guide_kernel(const double *cdf, uint32_t n_toa, uint32_t n_tables, uint32_t shift, uint32_t stride, uint32_t *guide) {
@@ -102,19 +112,27 @@ __global__ void test_path_kernel(const DevModel M, const double *in, uint32_t n,
   int rt = (int)x[1];
   v3 loc = V(x[2], x[3], x[4]);
   typename Cell::Path P;
-  double len = Cell::path(M, c, rt, loc, x[5], x[6], P);
-  Travel t = Cell::advance(M, c, rt, advance_mode ? x[7] : len, loc, x[5], x[6], P);
+  const v3 dir = from_thph(x[5], x[6]);
+  double len = Cell::path(M, c, rt, loc, dir, P);
+  Travel t = Cell::advance(M, c, rt, advance_mode ? x[7] : len, loc, dir, P);
   double *o = out + 9 * i;
-  o[0] = t.len; o[1] = t.time; o[2] = t.loc.x; o[3] = t.loc.y; o[4] = t.loc.z; o[5] = t.th; o[6] = t.ph; o[7] = t.atten;
+  o[0] = t.len; o[1] = t.time; o[2] = t.loc.x; o[3] = t.loc.y; o[4] = t.loc.z;
+  if (Cell::curved) angles_of(t.dir, o[5], o[6]); else { o[5] = x[5]; o[6] = x[6]; }
+  o[7] = exp(-t.aexp);
   o[8] = advance_mode ? -1.0 : (double)P.face;
 }
 __global__ void test_transform_kernel(const double *in, uint32_t n, double *out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double *x = in + 6 * i;
-  double th = x[0], ph = x[1], pol = x[2];
-  transform(th, ph, pol, x[3], x[4], x[5]);
-  out[3 * i] = th; out[3 * i + 1] = ph; out[3 * i + 2] = pol;
+  v3 e3 = from_thph(x[0], x[1]), s1 = s1_from_angles(x[0], x[1], x[2]);
+  double st, ct, sp, cp, sr, cr;
+  sincos(x[3], &st, &ct);
+  sincos(x[4], &sp, &cp);
+  sincos(x[5], &sr, &cr);
+  transform(e3, s1, st, ct, sp, cp, sr, cr);
+  angles_of(e3, out[3 * i], out[3 * i + 1]);
+  out[3 * i + 2] = pol_angle_of(e3, s1);
 }
 __global__ void test_rtcoef_kernel(const double *in, uint32_t n, double *out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,8 +157,9 @@ __global__ void test_catch_kernel(double bin_dt, uint32_t n_bins, const double *
   double *o = out + 6 * i;
   uint32_t bin = 0; double e[4] = {0, 0, 0, 0};
   int type = (int)x[25];
-  bool c = seis_catch(x, bin_dt, n_bins, x[18], V(x[19], x[20], x[21]), from_thph(x[22], x[23]),
-                      dir_of_motion(type, x[22], x[23], x[24]), type, x[26], x[27], bin, e);
+  const v3 dir = from_thph(x[22], x[23]);
+  bool c = seis_catch(x, bin_dt, n_bins, x[18], V(x[19], x[20], x[21]), dir,
+                      (type == R3D_RAY_P) ? dir : s1_from_angles(x[22], x[23], x[24]), type, x[26], x[27], bin, e);
   o[0] = c ? 1.0 : 0.0; o[1] = c ? (double)bin : -1.0; o[2] = e[0]; o[3] = e[1]; o[4] = e[2]; o[5] = e[3];
 }
 
@@ -343,7 +362,7 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   const double *th = nullptr, *ph = nullptr;
   if (int rc = dev_upload(D, &th, d->toa_theta, nt)) return rc;
   if (int rc = dev_upload(D, &ph, d->toa_phi, nt)) return rc;
-  double2 *toa = nullptr;
+  double4 *toa = nullptr;
   if (int rc = dev_alloc(D, &toa, nt)) return rc;
   pack_toa_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, D.stream>>>(th, ph, toa, (uint32_t)nt, d->min_theta, d->max_theta);
   M.toa = toa;
@@ -352,7 +371,14 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   if (int rc = dev_upload(D, &M.scat_mfp, d->scat_mfp, 2 * ns)) return rc;
   if (int rc = dev_upload(D, &M.scat_whole, d->scat_whole_cdf, 8 * ns)) return rc;
   if (int rc = dev_upload(D, &M.scat_cdf, d->scat_cdf, 4 * ns * nt)) return rc;
-  if (int rc = dev_upload(D, &M.scat_spol, d->scat_spol, ns * nt)) return rc;
+  {
+    const double *spol_raw = nullptr;
+    double2 *spol = nullptr;
+    if (int rc = dev_upload(D, &spol_raw, d->scat_spol, ns * nt)) return rc;
+    if (int rc = dev_alloc(D, &spol, ns * nt)) return rc;
+    pack_spol_kernel<<<(unsigned)((ns * nt + 255) / 256), 256, 0, D.stream>>>(spol_raw, spol, ns * nt);
+    M.scat_spol = spol;
+  }
   if (int rc = dev_upload(D, &M.cell_params, d->cell_params, nc * d->cell_nparam)) return rc;
   if (int rc = dev_upload(D, &M.cell_scat, d->cell_scat, nc)) return rc;
   if (int rc = dev_upload(D, &M.face_flags, d->face_flags, nc * nf)) return rc;
@@ -436,12 +462,12 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   // the pool
   Pool &Q = D.Q;
   memset(&Q, 0, sizeof Q);
-  long slots = env_int("R3D_POOL_SLOTS", 1 << 21);
+  long slots = env_int("R3D_POOL_SLOTS", 1 << 22);
   if (slots < 256) slots = 256;
   slots = (slots + 255) / 256 * 256;
   Q.n_slots = (uint32_t)slots;
   const size_t P = Q.n_slots;
-  double **dbl[] = {&Q.time, &Q.pathlen, &Q.recent, &Q.amp, &Q.lx, &Q.ly, &Q.lz, &Q.th, &Q.ph, &Q.pol};
+  double **dbl[] = {&Q.time, &Q.pathlen, &Q.recent, &Q.aexp, &Q.lx, &Q.ly, &Q.lz, &Q.dx, &Q.dy, &Q.dz, &Q.sx, &Q.sy, &Q.sz};
   for (double **a : dbl) if (int rc = dev_alloc(D, a, P)) return rc;
   uint32_t **u32[] = {&Q.moves, &Q.cell, &Q.ordinal, &Q.tr_catches, &Q.tr_scatters, &Q.tr_iters};
   for (uint32_t **a : u32) if (int rc = dev_alloc(D, a, P)) return rc;
@@ -450,7 +476,7 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   if (int rc = dev_alloc(D, &Q.idx, P)) return rc;
   if (int rc = dev_alloc(D, &Q.q_draw, P)) return rc;
   if (int rc = dev_alloc(D, &Q.q_face, P)) return rc;
-  if (int rc = dev_alloc(D, &Q.q_count, (size_t)4)) return rc;
+  if (int rc = dev_alloc(D, &Q.q_count, (size_t)R3D_Q_NCOUNT)) return rc;
   D.n_tally_rows = (uint32_t)(D.gridA + D.gridB + D.gridC);
   if (int rc = dev_alloc(D, &Q.block_tally, (size_t)D.n_tally_rows * R3D_NCOUNTERS)) return rc;
   CK(cudaMemsetAsync(Q.block_tally, 0, (size_t)D.n_tally_rows * R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
@@ -494,7 +520,7 @@ int run_job(DevState &D, const JobReq &jr) {
     }
     for (;;) {
       for (int k = 0; k < D.steps_per_batch; k++) {
-        CK(cudaMemsetAsync(Q.q_count, 0, 4 * sizeof(uint32_t), D.stream));
+        CK(cudaMemsetAsync(Q.q_count, 0, R3D_Q_NCOUNT * sizeof(uint32_t), D.stream));
         if (prof) CK(cudaEventRecord(D.prof_events[4 * k + 0], D.stream));
         fa<<<gridA, R3D_A_THREADS, D.smemA, D.stream>>>(D.M, Q, J, D.cells_in_smem);
         if (prof) CK(cudaEventRecord(D.prof_events[4 * k + 1], D.stream));
@@ -503,11 +529,11 @@ int run_job(DevState &D, const JobReq &jr) {
         fc<<<gridC, R3D_C_THREADS, D.smemC, D.stream>>>(D.M, Q, J, D.cells_in_smem, (uint32_t)(D.gridA + D.gridB));
         if (prof) {
           CK(cudaEventRecord(D.prof_events[4 * k + 3], D.stream));
-          CK(cudaMemcpyAsync(D.h_qcounts + 4 * k, Q.q_count, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, D.stream));
+          CK(cudaMemcpyAsync(D.h_qcounts + 4 * k, Q.q_count, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, D.stream));   // the four queue lengths
         }
         D.launches += 3; D.steps++;
       }
-      CK(cudaMemcpyAsync(D.h_flag, Q.q_count + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, D.stream));
+      CK(cudaMemcpyAsync(D.h_flag, Q.q_count + R3D_Q_ALIVE, sizeof(uint32_t), cudaMemcpyDeviceToHost, D.stream));
       CK(cudaStreamSynchronize(D.stream));
       CK(cudaGetLastError());
       if (prof) {
@@ -518,7 +544,7 @@ int run_job(DevState &D, const JobReq &jr) {
             CK(cudaEventElapsedTime(&ms, D.prof_events[4 * k + j], D.prof_events[4 * k + j + 1]));
             D.k_seconds[j] += ms * 1e-3;
             D.k_launches[j] += 1;
-            D.k_units[j] += (j == 0) ? 0 : D.h_qcounts[4 * k + (j - 1)];
+            D.k_units[j] += (j == 0) ? 0 : D.h_qcounts[4 * k + 2 * (j - 1)] + D.h_qcounts[4 * k + 2 * (j - 1) + 1];
           }
       }
       if (!*D.h_flag) break;               // the last advance step found no live phonon and had none to start

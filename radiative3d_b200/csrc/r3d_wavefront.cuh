@@ -23,33 +23,33 @@ namespace r3d {
 // ---- the pool (struct of arrays; one slot = one phonon in flight, phonons.hpp:69-126) -----------------------
 struct Pool {
   uint32_t n_slots;
-  double *time, *pathlen, *recent, *amp, *lx, *ly, *lz, *th, *ph, *pol;
+  double *time, *pathlen, *recent, *aexp;      // aexp: amplitude = exp(-aexp)
+  double *lx, *ly, *lz;                        // location
+  double *dx, *dy, *dz;                        // unit direction of travel            (e3)
+  double *sx, *sy, *sz;                        // unit polarisation direction         (s1; carried for P phonons too,
+                                               //  exactly as the reference carries mPol, phonons.hpp:109-118)
   uint32_t *moves, *cell, *ordinal;
   uint8_t *type, *alive;
   unsigned long long *idx;
   uint32_t *tr_catches, *tr_scatters, *tr_iters;   // per-phonon statistics, trace mode only
-  // queues (rebuilt every step)
+  // queues (rebuilt every step).  Both are filled from the two ends, so that the two kinds of entry never share a
+  // warp: scatter draws grow from index 0, source draws from index n_slots-1; P face hits from 0, S from n_slots-1.
   uint4 *q_draw;        // {slot, 31-bit draw, table index, kind}: kind 0 = source take-off angle, 1 = scatter angle
   uint2 *q_face;        // {slot, exit face}
-  uint32_t *q_count;    // [0] draws, [1] faces, [2] "some slot is alive" flag
+  uint32_t *q_count;    // R3D_Q_* below
   unsigned long long *block_tally;   // [n_blocks_max][R3D_NCOUNTERS], owned per block: no atomics
 };
+
+enum { R3D_Q_DRAW_SCAT = 0, R3D_Q_DRAW_SRC, R3D_Q_FACE_P, R3D_Q_FACE_S, R3D_Q_ALIVE, R3D_Q_CURSOR_DRAW, R3D_Q_CURSOR_FACE, R3D_Q_NCOUNT = 8 };
 
 struct Job { unsigned long long first, n, seed; r3d_phonon_final *finals; };
 
 struct Phonon {
-  double time, pathlen, recent, amp;
-  v3 loc;
-  double th, ph, pol;
+  double time, pathlen, recent, aexp;
+  v3 loc, dir, s1;
   uint32_t moves, cell;
   int type;
 };
-
-R3D_DEV void move(Phonon &p, const Travel &t) {   // Phonon::Move, phonons.cpp:62-70
-  p.pathlen += t.len; p.time += t.time; p.recent += t.time;
-  p.loc = t.loc; p.th = t.th; p.ph = t.ph;
-  p.amp *= t.atten; p.moves += 1;
-}
 
 // Rng positioned at an arbitrary ordinal (state is only the ordinal; the block is recomputed when needed)
 struct RngAt {
@@ -79,6 +79,18 @@ struct Tally {
       default: v[R3D_CNT_INVALID]++; v[7] |= (fate >> 8); break;
     }
   }
+  // barrier-free variant: each warp adds its sums to the block's row with atomics (rows are per block, so the only
+  // contention is between the few warps of one block, once per launch)
+  R3D_DEV void flush_warp(unsigned long long *row) {
+    const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int k = 0; k < R3D_NCOUNTERS; k++) {
+      unsigned long long x = v[k];
+      if (k == 7) { for (int o = 16; o > 0; o >>= 1) x |= __shfl_down_sync(R3D_FULL, x, o); }
+      else { for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(R3D_FULL, x, o); }
+      if (lane == 0 && x) { if (k == 7) atomicOr(row + k, x); else atomicAdd(row + k, x); }
+    }
+  }
   // all threads of the block must call this
   R3D_DEV void flush(unsigned long long *row, unsigned long long (*sm)[R3D_NCOUNTERS]) {
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -102,11 +114,18 @@ template <bool TRACE>
 R3D_DEV void write_final(const Pool &Q, const Job &J, uint32_t s, const Phonon &p, uint32_t fate, uint32_t ordinal) {
   if (!TRACE) return;
   r3d_phonon_final *f = J.finals + (Q.idx[s] - J.first);
-  f->time = p.time; f->pathlen = p.pathlen; f->amp = p.amp;
+  f->time = p.time; f->pathlen = p.pathlen; f->amp = exp(-p.aexp);
   f->loc[0] = p.loc.x; f->loc[1] = p.loc.y; f->loc[2] = p.loc.z;
-  f->theta = p.th; f->phi = p.ph; f->pol = p.pol;
+  angles_of(p.dir, f->theta, f->phi);
+  f->pol = pol_angle_of(p.dir, p.s1);
   f->moves = p.moves; f->cell = p.cell; f->type = (uint32_t)p.type; f->fate = fate;
   f->draws = ordinal; f->catches = Q.tr_catches[s]; f->scatters = Q.tr_scatters[s]; f->iters = Q.tr_iters[s];
+}
+
+// one 32-byte take-off-angle record through the read-only path (two 16-byte loads of the same sector)
+R3D_DEV double4 load_toa(const double4 *p) {
+  const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
 }
 
 // warp-aggregated queue append: one atomic per warp, consecutive positions for the lanes that push
@@ -119,6 +138,28 @@ R3D_DEV uint32_t queue_slot(uint32_t *counter, bool push) {
   if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
   base = __shfl_sync(R3D_FULL, base, leader);
   return base + __popc(mask & ((1u << lane) - 1u));
+}
+// two-ended queue of capacity cap: kind A entries at [0, nA), kind B entries at (cap - 1 - j), j in [0, nB)
+R3D_DEV uint32_t queue_slot2(uint32_t *counterA, uint32_t *counterB, uint32_t cap, bool pushA, bool pushB) {
+  const uint32_t a = queue_slot(counterA, pushA);
+  const uint32_t b = queue_slot(counterB, pushB);
+  return pushA ? a : cap - 1u - b;
+}
+// A warp pulls the next chunk of 32 logical entries of a two-ended queue.  Chunks [0, cA) cover kind A, chunks
+// [cA, cA + cB) kind B, so no warp mixes kinds.  Returns false when the queue is drained; else `at` is this lane's
+// entry index (valid iff `have`) and kindB tells which end it came from.
+R3D_DEV bool pull_chunk(uint32_t *cursor, uint32_t nA, uint32_t nB, uint32_t cap, uint32_t &at, bool &have, bool &kindB) {
+  const unsigned lane = threadIdx.x & 31u;
+  const uint32_t cA = (nA + 31u) >> 5, cB = (nB + 31u) >> 5;
+  uint32_t c = 0;
+  if (lane == 0) c = atomicAdd(cursor, 1u);
+  c = __shfl_sync(R3D_FULL, c, 0);
+  if (c >= cA + cB) return false;
+  kindB = c >= cA;
+  const uint32_t j = (kindB ? c - cA : c) * 32u + lane;
+  have = j < (kindB ? nB : nA);
+  at = kindB ? cap - 1u - j : j;
+  return true;
 }
 
 // CellFace::VelocityJump (media_cellface.cpp:83-99)
@@ -136,12 +177,16 @@ R3D_DEV double velocity_jump(const DevModel &M, const double *cells, uint32_t ce
 // kernel A: advance.  Grid-stride over tiles of blockDim.x pool slots.
 // =====================================================================================================
 #define R3D_A_THREADS 256
+#ifndef R3D_A_MINBLOCKS
+#define R3D_A_MINBLOCKS 4      // 64 registers: the kernel waits on HBM loads of the pool, resident warps hide them
+#endif
 template <class Cell, bool TRACE>
-__global__ void __launch_bounds__(R3D_A_THREADS)
+__global__ void __launch_bounds__(R3D_A_THREADS, R3D_A_MINBLOCKS)
 advance_kernel(const DevModel M, const Pool Q, const Job J, int cells_in_smem) {
   extern __shared__ double smem_cells[];
   __shared__ unsigned long long tally_sm[R3D_A_THREADS / 32][R3D_NCOUNTERS];
   __shared__ uint32_t warp_dead[R3D_A_THREADS / 32];
+  __shared__ uint32_t warp_push[R3D_A_THREADS / 32][4], push_base[4];
   __shared__ unsigned long long tile_base;
   if (cells_in_smem)
     for (uint32_t i = threadIdx.x; i < M.n_cells * M.cell_nparam; i += blockDim.x) smem_cells[i] = M.cell_params[i];
@@ -173,6 +218,7 @@ advance_kernel(const DevModel M, const Pool Q, const Job J, int cells_in_smem) {
     uint32_t fate = 0;
     bool push_draw = false, push_face = false;
     uint32_t draw_k = 0, draw_table = 0, draw_kind = 1u, face = 0;
+    int face_type = 0;
     if (dead) {
       const unsigned long long cand = tile_base + warp_dead[warp] + __popc(dmask & ((1u << lane) - 1u));
       if (cand < J.n) {
@@ -182,10 +228,9 @@ advance_kernel(const DevModel M, const Pool Q, const Job J, int cells_in_smem) {
         const uint32_t rt3 = cdf_search_small(M.src_whole, 3, g.next());
         draw_k = g.next();
         draw_table = rt3; draw_kind = 0u; push_draw = true;     // the take-off angle is drawn by this step's draw kernel
-        Q.time[s] = 0; Q.pathlen[s] = 0; Q.recent[s] = 0; Q.amp[s] = 1.0;
+        Q.time[s] = 0; Q.pathlen[s] = 0; Q.recent[s] = 0; Q.aexp[s] = 0.0;
         Q.lx[s] = M.src_loc[0]; Q.ly[s] = M.src_loc[1]; Q.lz[s] = M.src_loc[2];
-        Q.pol[s] = (rt3 == R3D_RAY_SH) ? kPi * 0.5 : 0.0;
-        Q.type[s] = (rt3 == R3D_RAY_P) ? R3D_RAY_P : R3D_RAY_S;
+        Q.type[s] = (rt3 == R3D_RAY_P) ? R3D_RAY_P : R3D_RAY_S;    // direction + polarisation: this step's draw kernel
         Q.moves[s] = 0; Q.cell[s] = M.src_cell; Q.ordinal[s] = 2; Q.idx[s] = idx; Q.alive[s] = 1;
         if (TRACE) { Q.tr_catches[s] = 0; Q.tr_scatters[s] = 0; Q.tr_iters[s] = 0; }
         T.v[6]++;
@@ -197,9 +242,9 @@ advance_kernel(const DevModel M, const Pool Q, const Job J, int cells_in_smem) {
     Phonon p;
     uint32_t ordinal = 0;
     if (alive) {
-      p.time = Q.time[s]; p.pathlen = Q.pathlen[s]; p.recent = Q.recent[s]; p.amp = Q.amp[s];
+      p.time = Q.time[s]; p.pathlen = Q.pathlen[s]; p.recent = Q.recent[s]; p.aexp = Q.aexp[s];
       p.loc = V(Q.lx[s], Q.ly[s], Q.lz[s]);
-      p.th = Q.th[s]; p.ph = Q.ph[s]; p.pol = Q.pol[s];
+      p.dir = V(Q.dx[s], Q.dy[s], Q.dz[s]);
       p.moves = Q.moves[s]; p.cell = Q.cell[s]; p.type = Q.type[s];
       ordinal = Q.ordinal[s];
       T.v[R3D_CNT_EVENTS]++;
@@ -218,11 +263,10 @@ advance_kernel(const DevModel M, const Pool Q, const Job J, int cells_in_smem) {
         if (why >= 0) fate = R3D_FATE_INVALID | ((1u << why) << 8);
         else { p.recent = 0; recent_reset = true; }
       }
-      (void)recent_reset;
       if (!fate) {
         const double *c = cells + (size_t)p.cell * M.cell_nparam;
         typename Cell::Path P;
-        const double edgelen = Cell::path(M, c, p.type, p.loc, p.th, p.ph, P);
+        const double edgelen = Cell::path(M, c, p.type, p.loc, p.dir, P);
         if (edgelen == pinf()) fate = R3D_FATE_TIMEOUT;       // phonons.cpp:595-598
         else {
           RngAt g; g.init(J.seed, Q.idx[s], ordinal);
@@ -231,12 +275,27 @@ advance_kernel(const DevModel M, const Pool Q, const Job J, int cells_in_smem) {
           const double r = 1.0 - ((double)g.next()) / (kRandMax + 1);
           const double scatlen = -log(r) * __ldg(M.scat_mfp + scat * 2 + p.type);
           const bool scatter = scatlen < edgelen;
-          Travel tr = Cell::advance(M, c, p.type, scatter ? scatlen : edgelen, p.loc, p.th, p.ph, P);
-          move(p, tr);
+          const Travel tr = Cell::advance(M, c, p.type, scatter ? scatlen : edgelen, p.loc, p.dir, P);
+          // Phonon::Move (phonons.cpp:62-70)
+          p.pathlen += tr.len; p.time += tr.time; p.recent += tr.time;
+          p.loc = tr.loc; p.aexp += tr.aexp; p.moves += 1;
+          if (Cell::curved) {            // the ray turned: the polarisation ANGLE is what the reference carries along
+            const v3 s1 = V(Q.sx[s], Q.sy[s], Q.sz[s]);
+            const v3 ns1 = carry_pol(p.dir, s1, tr.dir);
+            Q.sx[s] = ns1.x; Q.sy[s] = ns1.y; Q.sz[s] = ns1.z;
+            p.s1 = ns1;
+            p.dir = tr.dir;
+            Q.dx[s] = p.dir.x; Q.dy[s] = p.dir.y; Q.dz[s] = p.dir.z;
+          }
           if (scatter) {
             // Scatterer::GetRandomScatteredRelativePhonon (scatterers.cpp:318-363); the table draw is queued
             if (M.no_deflect) {
-              transform(p.th, p.ph, p.pol, M.min_theta, 0.0, 0.0);
+              if (!Cell::curved) p.s1 = V(Q.sx[s], Q.sy[s], Q.sz[s]);
+              double st, ct;
+              sincos(M.min_theta, &st, &ct);                  // Phonon(ThetaPhi(0,0)) nudged to min_theta, pol 0
+              transform(p.dir, p.s1, st, ct, 0.0, 1.0, 0.0, 1.0);
+              Q.dx[s] = p.dir.x; Q.dy[s] = p.dir.y; Q.dz[s] = p.dir.z;
+              Q.sx[s] = p.s1.x; Q.sy[s] = p.s1.y; Q.sz[s] = p.s1.z;
               T.v[R3D_CNT_SCATTERS]++;
               if (TRACE) Q.tr_scatters[s]++;
             } else {
@@ -249,6 +308,7 @@ advance_kernel(const DevModel M, const Pool Q, const Job J, int cells_in_smem) {
             const uint32_t fi = p.cell * M.faces_per_cell + P.face;
             const uint32_t fl = __ldg(M.face_flags + fi);
             face = P.face;
+            face_type = p.type;
             if (fl & (R3D_FACE_COLLECT | R3D_FACE_REFLECT)) push_face = true;
             else if (fl & R3D_FACE_ADJOIN) {                   // Phonon::Refract (phonons.cpp:225-255)
               const uint32_t other = __ldg(M.face_other + fi);
@@ -257,26 +317,46 @@ advance_kernel(const DevModel M, const Pool Q, const Job J, int cells_in_smem) {
             } else fate = R3D_FATE_LOST;                       // phonons.cpp:675
           }
           ordinal = g.g.ordinal;
-          Q.time[s] = p.time; Q.pathlen[s] = p.pathlen; Q.amp[s] = p.amp;
+          Q.time[s] = p.time; Q.pathlen[s] = p.pathlen; Q.aexp[s] = p.aexp;
           Q.lx[s] = p.loc.x; Q.ly[s] = p.loc.y; Q.lz[s] = p.loc.z;
-          Q.th[s] = p.th; Q.ph[s] = p.ph; Q.pol[s] = p.pol;
           Q.moves[s] = p.moves; Q.cell[s] = p.cell; Q.ordinal[s] = ordinal;
         }
       }
-      Q.recent[s] = p.recent;
+      if (recent_reset || !fate) Q.recent[s] = p.recent;
       if (fate) {
         Q.alive[s] = 0;
         T.died(fate);
+        if (TRACE) p.s1 = V(Q.sx[s], Q.sy[s], Q.sz[s]);
         write_final<TRACE>(Q, J, s, p, fate, ordinal);
       } else any_alive = true;
     }
-    // queue appends (warp-uniform calls)
-    uint32_t at = queue_slot(Q.q_count + 0, push_draw);
-    if (push_draw) Q.q_draw[at] = make_uint4(s, draw_k, draw_table, draw_kind);
-    at = queue_slot(Q.q_count + 1, push_face);
-    if (push_face) Q.q_face[at] = make_uint2(s, face);
+    // queue appends, aggregated over the tile: one atomic per queue end per 256 slots
+    {
+      const int qk = push_draw ? (draw_kind == 1u ? R3D_Q_DRAW_SCAT : R3D_Q_DRAW_SRC)
+                   : push_face ? (face_type == R3D_RAY_P ? R3D_Q_FACE_P : R3D_Q_FACE_S) : -1;
+      unsigned mine = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const unsigned m = __ballot_sync(R3D_FULL, qk == k);
+        if (lane == 0) warp_push[warp][k] = __popc(m);
+        if (qk == k) mine = m;
+      }
+      __syncthreads();
+      if (threadIdx.x < 4) {
+        uint32_t tot = 0;
+        for (unsigned w = 0; w < blockDim.x / 32; w++) { const uint32_t c = warp_push[w][threadIdx.x]; warp_push[w][threadIdx.x] = tot; tot += c; }
+        push_base[threadIdx.x] = tot ? atomicAdd(Q.q_count + threadIdx.x, tot) : 0u;
+      }
+      __syncthreads();
+      if (qk >= 0) {
+        const uint32_t j = push_base[qk] + warp_push[warp][qk] + __popc(mine & ((1u << lane) - 1u));
+        const uint32_t at = (qk == R3D_Q_DRAW_SCAT || qk == R3D_Q_FACE_P) ? j : Q.n_slots - 1u - j;
+        if (push_draw) Q.q_draw[at] = make_uint4(s, draw_k, draw_table, draw_kind);
+        else Q.q_face[at] = make_uint2(s, face);
+      }
+    }
   }
-  if (__syncthreads_or(any_alive) && threadIdx.x == 0) Q.q_count[2] = 1;
+  if (__syncthreads_or(any_alive) && threadIdx.x == 0) Q.q_count[R3D_Q_ALIVE] = 1;
   T.flush(Q.block_tally + (size_t)blockIdx.x * R3D_NCOUNTERS, tally_sm);
 }
 
@@ -288,30 +368,36 @@ advance_kernel(const DevModel M, const Pool Q, const Job J, int cells_in_smem) {
 template <bool TRACE>
 __global__ void __launch_bounds__(R3D_B_THREADS)
 draw_kernel(const DevModel M, const Pool Q, uint32_t tally_row0) {
-  __shared__ unsigned long long tally_sm[R3D_B_THREADS / 32][R3D_NCOUNTERS];
   Tally T; T.clear();
-  const uint32_t n = Q.q_count[0];
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  const uint32_t nA = Q.q_count[R3D_Q_DRAW_SCAT], nB = Q.q_count[R3D_Q_DRAW_SRC];
+  uint32_t i; bool have, is_src;
+  while (pull_chunk(Q.q_count + R3D_Q_CURSOR_DRAW, nA, nB, Q.n_slots, i, have, is_src)) {
+    if (!have) continue;
     const uint4 q = Q.q_draw[i];
     const uint32_t s = q.x;
-    if (q.w == 0u) {
+    if (is_src) {
+      // new phonon: direction = the drawn take-off angle, polarisation angle pi/2 for SH else 0 (phonons.hpp:193-207)
       const uint32_t ti = cdf_search(M.src_cdf + (size_t)q.z * M.n_toa, M.n_toa, M.src_guide + (size_t)q.z * M.guide_stride, M.guide_shift, q.y);
-      const double2 t = __ldg(M.toa + ti);
-      Q.th[s] = t.x; Q.ph[s] = t.y;
+      const double4 t = load_toa(M.toa + ti);                   // sin th, cos th, sin ph, cos ph
+      Q.dx[s] = t.x * t.w; Q.dy[s] = t.x * t.z; Q.dz[s] = t.y;
+      if (q.z == R3D_RAY_SH) { Q.sx[s] = -t.z; Q.sy[s] = t.w; Q.sz[s] = 0.0; }                 // phi-hat
+      else { Q.sx[s] = t.y * t.w; Q.sy[s] = t.y * t.z; Q.sz[s] = -t.x; }                      // theta-hat
     } else {
       const uint32_t ti = cdf_search(M.scat_cdf + (size_t)q.z * M.n_toa, M.n_toa, M.scat_guide + (size_t)q.z * M.guide_stride, M.guide_shift, q.y);
-      const double2 t = __ldg(M.toa + ti);
+      const double4 t = load_toa(M.toa + ti);
       const uint32_t conv = q.z & 3u;
-      const double rpol = (conv == 3u) ? __ldg(M.scat_spol + (size_t)(q.z >> 2) * M.n_toa + ti) : 0.0;
-      double th = Q.th[s], ph = Q.ph[s], pol = Q.pol[s];
-      transform(th, ph, pol, t.x, t.y, rpol);
-      Q.th[s] = th; Q.ph[s] = ph; Q.pol[s] = pol;
+      double2 rp = make_double2(1.0, 0.0);                        // (cos, sin) of the relative polarisation angle
+      if (conv == 3u) rp = __ldg(M.scat_spol + (size_t)(q.z >> 2) * M.n_toa + ti);
+      v3 e3 = V(Q.dx[s], Q.dy[s], Q.dz[s]), s1 = V(Q.sx[s], Q.sy[s], Q.sz[s]);
+      transform(e3, s1, t.x, t.y, t.z, t.w, rp.y, rp.x);
+      Q.dx[s] = e3.x; Q.dy[s] = e3.y; Q.dz[s] = e3.z;
+      Q.sx[s] = s1.x; Q.sy[s] = s1.y; Q.sz[s] = s1.z;
       Q.type[s] = (uint8_t)(conv & 1u);                       // PP,PS,SP,SS -> P,S,P,S
       T.v[R3D_CNT_SCATTERS]++;
       if (TRACE) Q.tr_scatters[s]++;
     }
   }
-  T.flush(Q.block_tally + (size_t)(tally_row0 + blockIdx.x) * R3D_NCOUNTERS, tally_sm);
+  T.flush_warp(Q.block_tally + (size_t)(tally_row0 + blockIdx.x) * R3D_NCOUNTERS);
 }
 
 // =====================================================================================================
@@ -320,13 +406,16 @@ draw_kernel(const DevModel M, const Pool Q, uint32_t tally_row0) {
 // Snell bending (phonons.cpp:311-405).
 // =====================================================================================================
 #define R3D_C_THREADS 128
+#ifndef R3D_C_MINBLOCKS
+#define R3D_C_MINBLOCKS 4      // 128 registers
+#endif
 
-// Phonon::Refraction_FullRT + CellFace::GetRTBasis (media_cellface.cpp:122-149)
+// Phonon::Refraction_FullRT (phonons.cpp:429-476) + CellFace::GetRTBasis (media_cellface.cpp:122-149)
 template <class Cell>
 R3D_DEV void refraction_fullrt(const DevModel &M, const double *cells, Phonon &p, int face, bool adjoin, uint32_t other, RngAt &g) {
   const double *c = cells + (size_t)p.cell * M.cell_nparam;
   RTCoef rt;
-  rt.init(Cell::normal(c, face, p.loc), from_thph(p.th, p.ph));
+  rt.init(Cell::normal(c, face, p.loc), p.dir);
   rt.densR = Cell::dens(c, p.loc);
   rt.velR[0] = Cell::veloc(c, 0, p.loc);
   rt.velR[1] = Cell::veloc(c, 1, p.loc);
@@ -339,17 +428,15 @@ R3D_DEV void refraction_fullrt(const DevModel &M, const double *cells, Phonon &p
     rt.densT = 0.0; rt.velT[0] = 1e-12; rt.velT[1] = 1e-12; rt.notransmit = true;
   }
   int intype = R3D_RAY_P;
-  if (p.type == R3D_RAY_S) intype = rt.choose_spol(dir_of_motion(p.type, p.th, p.ph, p.pol), g.next());
+  if (p.type == R3D_RAY_S) intype = rt.choose_spol(p.s1, g.next());        // DirectionOfMotion() of an S phonon is s1
   rt.get_coefs(intype);
   rt.choose(g.next());
   const bool reflected = (rt.choice == R_P || rt.choice == R_SV || rt.choice == R_SH);
-  v3 outdir = rt.chosen_ray_dir();
+  const v3 outdir = unit_else(rt.chosen_ray_dir(), V(0, 0, 1));          // mDir.Set(outdir.Theta(), outdir.Phi())
   p.type = (rt.choice == R_P || rt.choice == T_P) ? R3D_RAY_P : R3D_RAY_S;
-  p.th = xyz_theta(outdir); p.ph = xyz_phi(outdir);
-  if (p.type == R3D_RAY_S) {
-    v3 pdomo = rt.chosen_pdom();
-    p.pol = atan2(dot(pdomo, thph_phihat(p.ph)), dot(pdomo, thph_thetahat(p.th, p.ph)));
-  }
+  if (p.type == R3D_RAY_S) p.s1 = pol_from_pdom(outdir, rt.chosen_pdom());  // phonons.cpp:459-465
+  else p.s1 = carry_pol(p.dir, p.s1, outdir);                                 // mPol is left as it was
+  p.dir = outdir;
   if (!reflected) p.cell = other;
 }
 
@@ -358,40 +445,38 @@ template <class Cell>
 R3D_DEV void refraction_bend(const DevModel &M, const double *cells, Phonon &p, int face, uint32_t other) {
   const double *c = cells + (size_t)p.cell * M.cell_nparam;
   const double *o = cells + (size_t)other * M.cell_nparam;
-  v3 mdir = from_thph(p.th, p.ph);
-  v3 fnorm = Cell::normal(c, face, p.loc);
-  v3 fpara = inplane_unit_perp(fnorm, mdir);
-  v3 fparash = cross(fnorm, fpara);
-  double veli = Cell::veloc(c, p.type, p.loc), velo = Cell::veloc(o, p.type, p.loc);
-  double sini = dot(fpara, mdir);
+  const v3 mdir = p.dir;
+  const v3 fnorm = Cell::normal(c, face, p.loc);
+  const v3 fpara = inplane_unit_perp(fnorm, mdir);
+  const v3 fparash = cross(fnorm, fpara);
+  const double veli = Cell::veloc(c, p.type, p.loc), velo = Cell::veloc(o, p.type, p.loc);
+  const double sini = dot(fpara, mdir);
   double sino = (velo / veli) * sini;
   bool transfer; double coso;
   if (sino >= 1.0) { transfer = false; sino = sini; coso = -1.0 * dot(fnorm, mdir); }
   else { transfer = true; coso = sqrt(1.0 - (sino * sino)); }
-  v3 outdir = add(scal(fpara, sino), scal(fnorm, coso));
-  double polout = 0;
+  const v3 outraw = add(scal(fpara, sino), scal(fnorm, coso));
+  const v3 outdir = unit_else(outraw, V(0, 0, 1));
   if (p.type != R3D_RAY_P) {
-    v3 pdomi = dir_of_motion(p.type, p.th, p.ph, p.pol);
-    v3 svbasei = cross(fparash, mdir), svbaseo = cross(fparash, outdir);
-    double shcomi = dot(pdomi, fparash), svcomi = dot(pdomi, svbasei);
-    v3 pdomo = add(scal(fparash, shcomi), scal(svbaseo, svcomi));
-    polout = atan2(dot(pdomo, xyz_phihat(outdir)), dot(pdomo, xyz_thetahat(outdir)));
+    const v3 svbasei = cross(fparash, mdir), svbaseo = cross(fparash, outraw);
+    const double shcomi = dot(p.s1, fparash), svcomi = dot(p.s1, svbasei);
+    p.s1 = pol_from_pdom(outdir, add(scal(fparash, shcomi), scal(svbaseo, svcomi)));
+  } else {
+    p.s1 = hats(outdir).th;                     // polout = 0 for P (phonons.cpp:366, 393)
   }
-  p.th = xyz_theta(outdir); p.ph = xyz_phi(outdir);
-  p.pol = polout;
+  p.dir = outdir;
   if (transfer) p.cell = other;
 }
 
 template <class Cell, bool TRACE>
-__global__ void __launch_bounds__(R3D_C_THREADS, 4)
+__global__ void __launch_bounds__(R3D_C_THREADS, R3D_C_MINBLOCKS)
 interface_kernel(const DevModel M, const Pool Q, const Job J, int cells_in_smem, uint32_t tally_row0) {
   extern __shared__ double4 smem_c4[];
-  __shared__ unsigned long long tally_sm[R3D_C_THREADS / 32][R3D_NCOUNTERS];
   double4 *sph = smem_c4;                                     // [n_seis] (x, y, z, r_out^2 (1+eps))
   double *scells = reinterpret_cast<double *>(smem_c4 + M.n_seis);
-  const uint32_t n = Q.q_count[1];
+  const uint32_t nA = Q.q_count[R3D_Q_FACE_P], nB = Q.q_count[R3D_Q_FACE_S];
   Tally T; T.clear();
-  if (blockIdx.x * blockDim.x < n) {                          // blocks without work skip the table load
+  if (nA + nB > 0) {                                          // launches without work skip the table load
     for (uint32_t i = threadIdx.x; i < M.n_seis; i += blockDim.x) sph[i] = M.seis_sphere[i];
     if (cells_in_smem)
       for (uint32_t i = threadIdx.x; i < M.n_cells * M.cell_nparam; i += blockDim.x) scells[i] = M.cell_params[i];
@@ -399,19 +484,19 @@ interface_kernel(const DevModel M, const Pool Q, const Job J, int cells_in_smem,
   __syncthreads();
   const double *cells = cells_in_smem ? scells : M.cell_params;
 
-  const uint32_t n_round = (n + 31u) & ~31u;                  // whole warps stay in the loop together
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-    const bool have = i < n;
+  uint32_t i; bool have, is_s;
+  while (pull_chunk(Q.q_count + R3D_Q_CURSOR_FACE, nA, nB, Q.n_slots, i, have, is_s)) {
     uint32_t s = 0, fl = 0, other = 0, ordinal = 0;
     int face = 0;
     Phonon p;
-    p.time = p.pathlen = p.recent = p.amp = 0; p.loc = V(0, 0, 0); p.th = p.ph = p.pol = 0; p.moves = 0; p.cell = 0; p.type = 0;
+    p.time = p.pathlen = p.recent = p.aexp = 0; p.loc = V(0, 0, 0); p.dir = V(0, 0, 1); p.s1 = V(1, 0, 0); p.moves = 0; p.cell = 0; p.type = 0;
     if (have) {
       const uint2 q = Q.q_face[i];
       s = q.x; face = (int)q.y;
-      p.time = Q.time[s]; p.amp = Q.amp[s];
+      p.time = Q.time[s]; p.aexp = Q.aexp[s];
       p.loc = V(Q.lx[s], Q.ly[s], Q.lz[s]);
-      p.th = Q.th[s]; p.ph = Q.ph[s]; p.pol = Q.pol[s];
+      p.dir = V(Q.dx[s], Q.dy[s], Q.dz[s]);
+      p.s1 = V(Q.sx[s], Q.sy[s], Q.sz[s]);
       p.cell = Q.cell[s]; p.type = Q.type[s];
       ordinal = Q.ordinal[s];
       const uint32_t fi = p.cell * M.faces_per_cell + face;
@@ -436,10 +521,9 @@ interface_kernel(const DevModel M, const Pool Q, const Job J, int cells_in_smem,
           if (dx * dx + dy * dy + dz * dz > q.w) continue;       // cannot be within the gather radius
           // rare from here on (a few per cent of the surface hits): the exact CatchPhonon test
           const double vel = Cell::veloc(cells + (size_t)p.cell * M.cell_nparam, p.type, p.loc);
-          const v3 dir = from_thph(p.th, p.ph);
-          const v3 dopm = dir_of_motion(p.type, p.th, p.ph, p.pol);
+          const v3 dopm = (p.type == R3D_RAY_P) ? p.dir : p.s1;   // Phonon::DirectionOfMotion (phonons.cpp:201-211)
           uint32_t bin; double e[4];
-          if (seis_catch(M.seis + (size_t)k2 * R3D_SEIS_NPARAM, M.bin_dt, M.n_bins, p.time, p.loc, dir, dopm, p.type, p.amp, vel, bin, e)) {
+          if (seis_catch(M.seis + (size_t)k2 * R3D_SEIS_NPARAM, M.bin_dt, M.n_bins, p.time, p.loc, p.dir, dopm, p.type, exp(-p.aexp), vel, bin, e)) {
             const size_t b = (size_t)k2 * M.n_bins + bin;
             atomicAdd(M.energies + b * 5 + 0, e[0]);
             atomicAdd(M.energies + b * 5 + 1, e[1]);
@@ -470,12 +554,13 @@ interface_kernel(const DevModel M, const Pool Q, const Job J, int cells_in_smem,
         if (TRACE) { p.pathlen = Q.pathlen[s]; p.moves = Q.moves[s]; }
         write_final<TRACE>(Q, J, s, p, fate, g.g.ordinal);
       } else {
-        Q.th[s] = p.th; Q.ph[s] = p.ph; Q.pol[s] = p.pol;
+        Q.dx[s] = p.dir.x; Q.dy[s] = p.dir.y; Q.dz[s] = p.dir.z;
+        Q.sx[s] = p.s1.x; Q.sy[s] = p.s1.y; Q.sz[s] = p.s1.z;
         Q.cell[s] = p.cell; Q.type[s] = (uint8_t)p.type; Q.ordinal[s] = g.g.ordinal;
       }
     }
   }
-  T.flush(Q.block_tally + (size_t)(tally_row0 + blockIdx.x) * R3D_NCOUNTERS, tally_sm);
+  T.flush_warp(Q.block_tally + (size_t)(tally_row0 + blockIdx.x) * R3D_NCOUNTERS);
 }
 
 }  // namespace r3d

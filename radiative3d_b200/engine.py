@@ -39,7 +39,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or _LIB_PATH
+    p = path or os.environ.get("R3D_LIBRARY") or _LIB_PATH      # R3D_LIBRARY: a tuning build of the same library
     if not os.path.exists(p):
         raise FileNotFoundError(
             f"{p} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

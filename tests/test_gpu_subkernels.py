@@ -20,12 +20,22 @@ def free():
 
 
 def test_transform(free):
+    """Golden Transform vectors.  The reference ends Transform with theta' = acos(cos theta') (geom_r3.cpp:261), whose
+    absolute error is ~eps / sin(theta'): next to a pole that exceeds 1e-10 and it is the REFERENCE's value that is
+    off (the device keeps the frame as vectors).  So: compare the direction and polarisation VECTORS, with the
+    tolerance widened by that conditioning term."""
     out = engine.transform(free["transform_in"])
     ref = free["transform_out"]
-    # angles: compare as angles (phi, pol wrap at +-pi)
-    d = np.abs(out - ref)
-    d[:, 1:] = np.minimum(d[:, 1:], 2 * np.pi - d[:, 1:])
-    assert d.max() <= TOL * np.pi
+
+    def frame(a):
+        st, ct, sp, cp, sr, cr = np.sin(a[:, 0]), np.cos(a[:, 0]), np.sin(a[:, 1]), np.cos(a[:, 1]), np.sin(a[:, 2]), np.cos(a[:, 2])
+        return (np.stack([st * cp, st * sp, ct], 1), np.stack([cr * ct * cp - sr * sp, cr * ct * sp + sr * cp, -cr * st], 1))
+
+    (e3a, s1a), (e3b, s1b) = frame(out), frame(ref)
+    tol = TOL + 16 * np.finfo(float).eps / np.maximum(np.sin(ref[:, 0]), 1e-12)
+    assert (np.abs(e3a - e3b).max(axis=1) <= tol).all()
+    assert (np.abs(s1a - s1b).max(axis=1) <= tol).all()
+    assert (tol <= TOL * 1.01).mean() > 0.95           # the widening only touches the few near-pole cases
 
 
 def test_transform_random_vs_oracle():
