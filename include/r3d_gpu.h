@@ -222,11 +222,15 @@ int r3d_stream(r3d_handle *h, int dev_slot, void **stream);
 /* Number of kernels this handle has launched so far. */
 int r3d_launch_count(r3d_handle *h, uint64_t *n);
 
-/* Per-kernel timing for the roofline report.  While profiling is on, every kernel launch of the step loop
- * is bracketed by CUDA events on the launching stream (this slows the loop down a little, so timed
- * throughput runs leave it off).  r3d_kernel_times returns, for device slot 0, the accumulated device
- * seconds and launch counts of [0] the advance kernel, [1] the draw kernel, [2] the interface kernel, and
- * the number of units each processed: [0] live phonons advanced, [1] table draws, [2] face events. */
+/* Kernel timing for the roofline report.  Every launch of the propagate kernel is bracketed by CUDA events on
+ * the launching stream, and every CTA counts the clock cycles it spends in its two phases.  r3d_set_profiling
+ * resets these totals (`on` is ignored).  r3d_kernel_times returns, for device slot 0 since the last reset:
+ *   seconds[0]  device seconds of the propagate kernel launches
+ *   seconds[1]  the share of seconds[0] spent in phase 1 (advance + refill), averaged over CTAs
+ *   seconds[2]  the share spent in phase 2 (table draws + face events)
+ *   launches[0] kernel launches, launches[1] iterations of the busiest CTA, launches[2] CTAs per launch
+ *   units[0]    propagate-loop events, units[1] table draws (scatter + source), units[2] bin updates
+ * units are read from the handle's counters, so call r3d_reset together with r3d_set_profiling. */
 int r3d_set_profiling(r3d_handle *h, int on);
 int r3d_kernel_times(r3d_handle *h, double seconds[3], uint64_t launches[3], uint64_t units[3]);
 

@@ -1,10 +1,10 @@
 // r3d_gpu.cu -- the C ABI of include/r3d_gpu.h and the host side of the propagate path (sm_100a only).
 //
-// The device work is in r3d_wavefront.cuh (three kernels per step over a pool of phonons in HBM) and
-// r3d_device.cuh (the physics).  This file uploads a flattened model, builds the exact guide tables for the
-// CDF searches, and drives the step loop: every device of a handle has one worker thread that enqueues
-// batches of steps on the device's stream and polls a device flag between batches, so r3d_run() returns at
-// once and devices run concurrently.  There is no CPU fallback anywhere in this file.
+// The device work is in r3d_resident.cuh (one persistent kernel; the phonons live in shared memory) and
+// r3d_device.cuh (the physics).  This file uploads a flattened model into one device arena, builds the exact
+// guide tables for the CDF searches, and launches one kernel per job: every device of a handle has one worker
+// thread that launches queued jobs on the device's stream, so r3d_run() returns at once and devices run
+// concurrently.  There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -19,7 +19,7 @@
 #include <stdlib.h>
 #include "r3d_gpu.h"
 #include "r3d_device.cuh"
-#include "r3d_wavefront.cuh"
+#include "r3d_resident.cuh"
 
 using namespace r3d;
 
@@ -172,16 +172,16 @@ struct DevState {
   int device = -1;
   cudaStream_t stream = nullptr;
   DevModel M;
-  Pool Q;
   uint32_t cell_kind = 0;
   std::vector<void *> allocs;
-  int gridA = 0, gridB = 0, gridC = 0;
-  size_t smemA = 0, smemC = 0;
-  int cells_in_smem = 0;
-  uint32_t n_tally_rows = 0;
-  uint32_t *h_flag = nullptr;              // pinned
-  int steps_per_batch = 16;
-  // worker thread: runs the step loop of queued jobs on this device's stream
+  // launch geometry of the persistent kernel
+  int grid = 0, threads = 0, blocks_per_sm = 1;
+  size_t smem_block = 0;                   // dynamic shared memory available to one CTA
+  uint32_t cell_doubles = 0;               // cell parameters staged in shared memory (0: read from global memory)
+  uint32_t max_slots[2] = {0, 0};          // slots per CTA that fit [plain | trace]
+  unsigned long long *block_tally = nullptr;   // [grid][R3D_NCOUNTERS], one row per CTA: no atomics
+  unsigned long long *block_clock = nullptr;   // [grid][3]: cycles in phase 1, cycles in phase 2, iterations
+  // worker thread: launches queued jobs on this device's stream
   std::thread worker;
   std::mutex mu;
   std::condition_variable cv;
@@ -191,13 +191,9 @@ struct DevState {
   int err_code = 0;
   std::string err;
   double seconds = 0;                      // device time of the jobs finished since the last r3d_sync
-  unsigned long long launches = 0, steps = 0;
-  // optional per-kernel timing (r3d_set_profiling)
-  bool profiling = false;
-  std::vector<cudaEvent_t> prof_events;    // 4 per step of a batch
-  uint32_t *h_qcounts = nullptr;           // pinned: [steps_per_batch][4] copies of q_count
-  double k_seconds[3] = {0, 0, 0};
-  unsigned long long k_launches[3] = {0, 0, 0}, k_units[3] = {0, 0, 0};
+  unsigned long long launches = 0;
+  double k_seconds = 0;                    // device time of the propagate kernel alone since r3d_set_profiling
+  unsigned long long k_launches = 0;
 };
 
 }  // namespace
@@ -226,24 +222,14 @@ int dev_upload(DevState &D, const T **p, const T *host, size_t count) {
   return 0;
 }
 
-typedef void (*advance_fn)(const DevModel, const Pool, const Job, int);
-typedef void (*draw_fn)(const DevModel, const Pool, uint32_t);
-typedef void (*interface_fn)(const DevModel, const Pool, const Job, int, uint32_t);
-advance_fn pick_advance(uint32_t kind, bool trace) {
+typedef void (*propagate_fn)(const DevModel, const Job, uint32_t, uint32_t, unsigned long long *, unsigned long long *);
+propagate_fn pick_propagate(uint32_t kind, bool trace) {
   switch (kind) {
-    case R3D_CELL_CYLINDER: return trace ? advance_kernel<Cylinder, true> : advance_kernel<Cylinder, false>;
-    case R3D_CELL_SHELL: return trace ? advance_kernel<Shell, true> : advance_kernel<Shell, false>;
-    default: return trace ? advance_kernel<Tetra, true> : advance_kernel<Tetra, false>;
+    case R3D_CELL_CYLINDER: return trace ? propagate_kernel<Cylinder, true> : propagate_kernel<Cylinder, false>;
+    case R3D_CELL_SHELL: return trace ? propagate_kernel<Shell, true> : propagate_kernel<Shell, false>;
+    default: return trace ? propagate_kernel<Tetra, true> : propagate_kernel<Tetra, false>;
   }
 }
-interface_fn pick_interface(uint32_t kind, bool trace) {
-  switch (kind) {
-    case R3D_CELL_CYLINDER: return trace ? interface_kernel<Cylinder, true> : interface_kernel<Cylinder, false>;
-    case R3D_CELL_SHELL: return trace ? interface_kernel<Shell, true> : interface_kernel<Shell, false>;
-    default: return trace ? interface_kernel<Tetra, true> : interface_kernel<Tetra, false>;
-  }
-}
-draw_fn pick_draw(bool trace) { return trace ? draw_kernel<true> : draw_kernel<false>; }
 
 int validate(const r3d_model_desc *d) {
   if (!d) return fail(R3D_EINVAL, "null model descriptor");
@@ -433,132 +419,77 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   CK(cudaMemsetAsync(M.counts, 0, nb * R3D_BIN_NCNT * sizeof(unsigned long long), D.stream));
   CK(cudaMemsetAsync(M.counters, 0, R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
 
-  // launch geometry: grid-stride kernels sized to a whole number of resident CTAs per SM
+  // launch geometry: persistent CTAs, `blocks_per_sm` per SM, each with an equal share of the SM's shared memory
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, D.device));
+  D.threads = std::min(R3D_NT, std::max(32, env_int("R3D_THREADS", 512) / 32 * 32));
+  D.blocks_per_sm = std::max(1, env_int("R3D_BLOCKS_PER_SM", 1));
+  cudaFuncAttributes fattr;
+  CK(cudaFuncGetAttributes(&fattr, pick_propagate(d->cell_kind, true)));
+  const size_t per_block = (size_t)prop.sharedMemPerMultiprocessor / D.blocks_per_sm - (size_t)prop.reservedSharedMemPerBlock - fattr.sharedSizeBytes;
+  D.smem_block = std::min(per_block, (size_t)prop.sharedMemPerBlockOptin - fattr.sharedSizeBytes) / 16 * 16;
   const size_t cell_bytes = nc * d->cell_nparam * sizeof(double);
-  D.cells_in_smem = cell_bytes <= 16 * 1024;
-  D.smemA = D.cells_in_smem ? cell_bytes : 0;
-  D.smemC = (size_t)d->n_seis * sizeof(double4) + (D.cells_in_smem ? cell_bytes : 0);
-  if (D.smemC > (size_t)prop.sharedMemPerBlockOptin)
-    return fail(R3D_EUNSUPPORTED, "too many seismometers for the shared-memory scan table");
-  int occA = 1, occB = 1, occC = 1;
-  for (int trace = 0; trace < 2; trace++) {
-    advance_fn fa = pick_advance(d->cell_kind, trace != 0);
-    interface_fn fc = pick_interface(d->cell_kind, trace != 0);
-    CK(cudaFuncSetAttribute(fa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smemA));
-    CK(cudaFuncSetAttribute(fc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smemC));
-    if (trace == 0) {
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, fa, R3D_A_THREADS, D.smemA));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, pick_draw(false), R3D_B_THREADS, 0));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occC, fc, R3D_C_THREADS, D.smemC));
-    }
+  D.cell_doubles = 0;                      // cell parameters are read through L1 (r3d_resident.cuh)
+  (void)cell_bytes;
+  const size_t for_slots = D.smem_block - (size_t)D.cell_doubles * 8;
+  D.max_slots[0] = (uint32_t)std::min<size_t>(for_slots / R3D_SLOT_BYTES / 32 * 32, 65504);
+  D.max_slots[1] = (uint32_t)std::min<size_t>(for_slots / R3D_SLOT_BYTES_TRACE / 32 * 32, 65504);
+  if (int cap = env_int("R3D_SLOTS_PER_BLOCK", 0)) {
+    for (int t = 0; t < 2; t++) D.max_slots[t] = std::max(32u, std::min(D.max_slots[t], (uint32_t)cap / 32 * 32));
   }
-  const int sms = prop.multiProcessorCount;
-  D.gridA = sms * std::max(occA, 1);
-  D.gridB = sms * std::max(occB, 1);
-  D.gridC = sms * std::max(occC, 1);
-
-  // the pool
-  Pool &Q = D.Q;
-  memset(&Q, 0, sizeof Q);
-  long slots = env_int("R3D_POOL_SLOTS", 1 << 22);
-  if (slots < 256) slots = 256;
-  slots = (slots + 255) / 256 * 256;
-  Q.n_slots = (uint32_t)slots;
-  const size_t P = Q.n_slots;
-  double **dbl[] = {&Q.time, &Q.pathlen, &Q.recent, &Q.aexp, &Q.lx, &Q.ly, &Q.lz, &Q.dx, &Q.dy, &Q.dz, &Q.sx, &Q.sy, &Q.sz};
-  for (double **a : dbl) if (int rc = dev_alloc(D, a, P)) return rc;
-  uint32_t **u32[] = {&Q.moves, &Q.cell, &Q.ordinal, &Q.tr_catches, &Q.tr_scatters, &Q.tr_iters};
-  for (uint32_t **a : u32) if (int rc = dev_alloc(D, a, P)) return rc;
-  if (int rc = dev_alloc(D, &Q.type, P)) return rc;
-  if (int rc = dev_alloc(D, &Q.alive, P)) return rc;
-  if (int rc = dev_alloc(D, &Q.idx, P)) return rc;
-  if (int rc = dev_alloc(D, &Q.q_draw, P)) return rc;
-  if (int rc = dev_alloc(D, &Q.q_face, P)) return rc;
-  if (int rc = dev_alloc(D, &Q.q_count, (size_t)R3D_Q_NCOUNT)) return rc;
-  D.n_tally_rows = (uint32_t)(D.gridA + D.gridB + D.gridC);
-  if (int rc = dev_alloc(D, &Q.block_tally, (size_t)D.n_tally_rows * R3D_NCOUNTERS)) return rc;
-  CK(cudaMemsetAsync(Q.block_tally, 0, (size_t)D.n_tally_rows * R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
-  CK(cudaMemsetAsync(Q.alive, 0, P, D.stream));
-  CK(cudaMallocHost(&D.h_flag, sizeof(uint32_t)));
-  D.steps_per_batch = std::max(1, env_int("R3D_STEPS_PER_BATCH", 16));
+  if (D.max_slots[1] < 32) return fail(R3D_EUNSUPPORTED, "shared memory too small for the phonon slots");
+  for (int trace = 0; trace < 2; trace++)
+    CK(cudaFuncSetAttribute(pick_propagate(d->cell_kind, trace != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_block));
+  D.grid = prop.multiProcessorCount * D.blocks_per_sm;
+  if (int rc = dev_alloc(D, &D.block_tally, (size_t)D.grid * R3D_NCOUNTERS)) return rc;
+  if (int rc = dev_alloc(D, &D.block_clock, (size_t)D.grid * 3)) return rc;
+  CK(cudaMemsetAsync(D.block_tally, 0, (size_t)D.grid * R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
+  CK(cudaMemsetAsync(D.block_clock, 0, (size_t)D.grid * 3 * sizeof(unsigned long long), D.stream));
 
   CK(cudaStreamSynchronize(D.stream));
   CK(cudaGetLastError());
   return 0;
 }
 
-// The step loop of one job on one device (called on the device's worker thread).
+// One job on one device (called on the device's worker thread): one launch of the persistent kernel.
 int run_job(DevState &D, const JobReq &jr) {
   CK(cudaSetDevice(D.device));
-  cudaEvent_t ev0, ev1;
+  cudaEvent_t ev0, ev1, ek0, ek1;
   CK(cudaEventCreate(&ev0));
   CK(cudaEventCreate(&ev1));
+  CK(cudaEventCreate(&ek0));
+  CK(cudaEventCreate(&ek1));
   CK(cudaEventRecord(ev0, D.stream));
   if (jr.n) {
     const bool trace = jr.finals != nullptr;
-    Pool Q = D.Q;
-    // no more slots than phonons (a small job keeps its whole population in flight at once)
-    const unsigned long long want = (jr.n + 255ull) / 256ull * 256ull;
-    if (want < Q.n_slots) Q.n_slots = (uint32_t)want;
     Job J; J.first = jr.first; J.n = jr.n; J.seed = jr.seed; J.finals = jr.finals;
-    const uint32_t n_tiles = Q.n_slots / R3D_A_THREADS;
-    const int gridA = (int)std::min<uint32_t>((uint32_t)D.gridA, n_tiles);
-    const int gridB = (int)std::min<uint32_t>((uint32_t)D.gridB, (Q.n_slots + R3D_B_THREADS - 1) / R3D_B_THREADS);
-    const int gridC = (int)std::min<uint32_t>((uint32_t)D.gridC, (Q.n_slots + R3D_C_THREADS - 1) / R3D_C_THREADS);
-    advance_fn fa = pick_advance(D.cell_kind, trace);
-    draw_fn fb = pick_draw(trace);
-    interface_fn fc = pick_interface(D.cell_kind, trace);
+    // no more slots than phonons: a small job is spread over all CTAs instead of filling the first few
+    uint32_t S = D.max_slots[trace ? 1 : 0];
+    const unsigned long long share = (jr.n + (unsigned long long)D.grid - 1) / (unsigned long long)D.grid;
+    if (share < S) S = (uint32_t)((share + 31ull) / 32ull * 32ull);
+    const size_t smem = (size_t)S * (trace ? R3D_SLOT_BYTES_TRACE : R3D_SLOT_BYTES) + (size_t)D.cell_doubles * 8;
+    const unsigned long long need = (jr.n + S - 1) / S;
+    const int grid = (int)std::min<unsigned long long>((unsigned long long)D.grid, need);
     CK(cudaMemsetAsync(D.M.next_phonon, 0, sizeof(unsigned long long), D.stream));
-    CK(cudaMemsetAsync(Q.alive, 0, Q.n_slots, D.stream));
-    const bool prof = D.profiling;
-    if (prof && D.prof_events.empty()) {
-      D.prof_events.resize((size_t)4 * D.steps_per_batch);
-      for (auto &ev : D.prof_events) CK(cudaEventCreate(&ev));
-      CK(cudaMallocHost(&D.h_qcounts, (size_t)4 * D.steps_per_batch * sizeof(uint32_t)));
-    }
-    for (;;) {
-      for (int k = 0; k < D.steps_per_batch; k++) {
-        CK(cudaMemsetAsync(Q.q_count, 0, R3D_Q_NCOUNT * sizeof(uint32_t), D.stream));
-        if (prof) CK(cudaEventRecord(D.prof_events[4 * k + 0], D.stream));
-        fa<<<gridA, R3D_A_THREADS, D.smemA, D.stream>>>(D.M, Q, J, D.cells_in_smem);
-        if (prof) CK(cudaEventRecord(D.prof_events[4 * k + 1], D.stream));
-        fb<<<gridB, R3D_B_THREADS, 0, D.stream>>>(D.M, Q, (uint32_t)D.gridA);
-        if (prof) CK(cudaEventRecord(D.prof_events[4 * k + 2], D.stream));
-        fc<<<gridC, R3D_C_THREADS, D.smemC, D.stream>>>(D.M, Q, J, D.cells_in_smem, (uint32_t)(D.gridA + D.gridB));
-        if (prof) {
-          CK(cudaEventRecord(D.prof_events[4 * k + 3], D.stream));
-          CK(cudaMemcpyAsync(D.h_qcounts + 4 * k, Q.q_count, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, D.stream));   // the four queue lengths
-        }
-        D.launches += 3; D.steps++;
-      }
-      CK(cudaMemcpyAsync(D.h_flag, Q.q_count + R3D_Q_ALIVE, sizeof(uint32_t), cudaMemcpyDeviceToHost, D.stream));
-      CK(cudaStreamSynchronize(D.stream));
-      CK(cudaGetLastError());
-      if (prof) {
-        std::lock_guard<std::mutex> lk(D.mu);
-        for (int k = 0; k < D.steps_per_batch; k++)
-          for (int j = 0; j < 3; j++) {
-            float ms = 0;
-            CK(cudaEventElapsedTime(&ms, D.prof_events[4 * k + j], D.prof_events[4 * k + j + 1]));
-            D.k_seconds[j] += ms * 1e-3;
-            D.k_launches[j] += 1;
-            D.k_units[j] += (j == 0) ? 0 : D.h_qcounts[4 * k + 2 * (j - 1)] + D.h_qcounts[4 * k + 2 * (j - 1) + 1];
-          }
-      }
-      if (!*D.h_flag) break;               // the last advance step found no live phonon and had none to start
-    }
+    CK(cudaEventRecord(ek0, D.stream));
+    pick_propagate(D.cell_kind, trace)<<<grid, D.threads, smem, D.stream>>>(D.M, J, S, D.cell_doubles, D.block_tally, D.block_clock);
+    CK(cudaEventRecord(ek1, D.stream));
+    D.launches += 1;
   }
-  reduce_tally_kernel<<<R3D_NCOUNTERS, 256, 0, D.stream>>>(D.Q.block_tally, D.n_tally_rows, D.M.counters);
+  reduce_tally_kernel<<<R3D_NCOUNTERS, 256, 0, D.stream>>>(D.block_tally, (uint32_t)D.grid, D.M.counters);
   D.launches += 1;
   CK(cudaEventRecord(ev1, D.stream));
   CK(cudaStreamSynchronize(D.stream));
   CK(cudaGetLastError());
-  float ms = 0;
+  float ms = 0, kms = 0;
   CK(cudaEventElapsedTime(&ms, ev0, ev1));
-  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
-  { std::lock_guard<std::mutex> lk(D.mu); D.seconds += ms * 1e-3; }
+  if (jr.n) CK(cudaEventElapsedTime(&kms, ek0, ek1));
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ek0); cudaEventDestroy(ek1);
+  {
+    std::lock_guard<std::mutex> lk(D.mu);
+    D.seconds += ms * 1e-3;
+    if (jr.n) { D.k_seconds += kms * 1e-3; D.k_launches += 1; }
+  }
   return 0;
 }
 
@@ -617,9 +548,6 @@ void destroy_device(DevState *D) {
     cudaSetDevice(D->device);
     if (D->stream) cudaStreamSynchronize(D->stream);
     for (void *p : D->allocs) cudaFree(p);
-    if (D->h_flag) cudaFreeHost(D->h_flag);
-    if (D->h_qcounts) cudaFreeHost(D->h_qcounts);
-    for (auto &ev : D->prof_events) cudaEventDestroy(ev);
     if (D->stream) cudaStreamDestroy(D->stream);
   }
   delete D;
@@ -739,7 +667,7 @@ int r3d_reset(r3d_handle *h) {
     CK(cudaMemsetAsync(D.M.energies, 0, nb * R3D_BIN_NF64 * sizeof(double), D.stream));
     CK(cudaMemsetAsync(D.M.counts, 0, nb * R3D_BIN_NCNT * sizeof(unsigned long long), D.stream));
     CK(cudaMemsetAsync(D.M.counters, 0, R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
-    CK(cudaMemsetAsync(D.Q.block_tally, 0, (size_t)D.n_tally_rows * R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
+    CK(cudaMemsetAsync(D.block_tally, 0, (size_t)D.grid * R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
     CK(cudaStreamSynchronize(D.stream));
   }
   return 0;
@@ -769,11 +697,14 @@ int r3d_launch_count(r3d_handle *h, uint64_t *n) {
 
 int r3d_set_profiling(r3d_handle *h, int on) {
   if (!h) return fail(R3D_EINVAL, "null handle");
+  (void)on;                                 // the kernel is always timed; this call resets the totals
   for (DevState *D : h->devs) {
     if (int rc = drain(*D)) return rc;
+    CK(cudaSetDevice(D->device));
+    CK(cudaMemsetAsync(D->block_clock, 0, (size_t)D->grid * 3 * sizeof(unsigned long long), D->stream));
+    CK(cudaStreamSynchronize(D->stream));
     std::lock_guard<std::mutex> lk(D->mu);
-    D->profiling = on != 0;
-    for (int j = 0; j < 3; j++) { D->k_seconds[j] = 0; D->k_launches[j] = 0; D->k_units[j] = 0; }
+    D->k_seconds = 0; D->k_launches = 0;
   }
   return 0;
 }
@@ -785,9 +716,19 @@ int r3d_kernel_times(r3d_handle *h, double seconds[3], uint64_t launches[3], uin
   unsigned long long k[R3D_NCOUNTERS];
   CK(cudaSetDevice(D.device));
   CK(cudaMemcpy(k, D.M.counters, sizeof k, cudaMemcpyDeviceToHost));
+  std::vector<unsigned long long> clk((size_t)D.grid * 3);
+  CK(cudaMemcpy(clk.data(), D.block_clock, clk.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  unsigned long long c1 = 0, c2 = 0, it = 0;
+  for (int b = 0; b < D.grid; b++) { c1 += clk[3 * b]; c2 += clk[3 * b + 1]; it = std::max(it, clk[3 * b + 2]); }
   std::lock_guard<std::mutex> lk(D.mu);
-  for (int j = 0; j < 3; j++) { seconds[j] = D.k_seconds[j]; launches[j] = D.k_launches[j]; units[j] = D.k_units[j]; }
-  units[0] = k[R3D_CNT_EVENTS];            // live phonons advanced == loop events tallied by the advance kernel
+  const double tot = (double)(c1 + c2);
+  seconds[0] = D.k_seconds;                                   // the propagate kernel, CUDA events on its stream
+  seconds[1] = tot > 0 ? D.k_seconds * (double)c1 / tot : 0;  // of which phase 1 (advance + refill), CTA-averaged
+  seconds[2] = tot > 0 ? D.k_seconds * (double)c2 / tot : 0;  // of which phase 2 (table draws + face events)
+  launches[0] = D.k_launches; launches[1] = it; launches[2] = (uint64_t)D.grid;
+  units[0] = k[R3D_CNT_EVENTS];
+  units[1] = k[R3D_CNT_SCATTERS] + k[6];                      // table draws = scatter draws + source draws
+  units[2] = k[R3D_CNT_CATCHES];
   return 0;
 }
 

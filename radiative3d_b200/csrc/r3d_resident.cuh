@@ -1,0 +1,611 @@
+// r3d_resident.cuh -- the propagate loop as a block-local wavefront over phonons that LIVE IN SHARED MEMORY.
+//
+// One iteration of the reference's Propagate loop (phonons.cpp:542) is one of a few very different events
+// (scatter / cell-to-cell hand-over / surface reflection with a seismometer scan / loss / time-out / new phonon).
+// Two earlier designs and what ncu said about them (profiles/):
+//   * one phonon per thread in one fused loop: a warp holds all event kinds at once -- 5.3 of 32 lanes active,
+//     instruction-fetch stalls (profiles/r1_fused_kernel.md);
+//   * a wavefront over a phonon pool in HBM, three kernels per step with global index queues: lanes converge, but
+//     the draw and interface kernels touch a sparse subset of the struct-of-arrays pool, so every 8-byte field
+//     costs a 32-byte sector: 400 B of DRAM traffic per draw and 1.1 kB per face event, 50-67 % of DRAM
+//     bandwidth spent on state that is never reused by another SM (profiles/r1_wavefront_hbm.md).
+// Here every CTA is persistent and owns S phonon slots in its shared memory (144 B per slot, ~1500 slots in the
+// 227 KB of a B200 SM).  The CTA alternates two phases, separated by __syncthreads():
+//   phase 1  advance  (slots ready to move)  time-out / validity checks, distance to boundary, path-length draw,
+//                                            move, cheap hand-overs inline; classification of the event
+//            refill   (free slots)           new phonon indices from the global work counter; source ray type
+//   phase 2  draw     (queued table draws)   exact guide-table CDF search + take-off-angle fetch from HBM/L2, then
+//                                            the new phonon's direction or Phonon::Transform
+//            face     (queued face events)   seismometer catch through the uniform-grid index, R/T coefficients,
+//                                            ray bending
+// Within a phase, warps pull 32-entry chunks of ONE kind of work from index queues in shared memory, so a warp
+// executes one kind of event (P and S face events are queued apart, source and scatter draws too).  State never
+// leaves the SM; HBM sees only the table gathers (~150 B per draw) and the bin atomics.  Several CTAs per SM
+// (R3D_BLOCKS_PER_SM) run in different phases and fill each other's barrier bubbles.
+#pragma once
+#include "r3d_device.cuh"
+
+namespace r3d {
+
+#define R3D_FULL 0xffffffffu
+#ifndef R3D_NT
+#define R3D_NT 512             // upper bound of threads per CTA (the launch may use fewer)
+#endif
+#ifndef R3D_MINBLOCKS
+#define R3D_MINBLOCKS 1        // 512 x 1 => 128 registers per thread; 256 threads x 2 CTAs per SM uses the same budget
+#endif
+
+struct Job { unsigned long long first, n, seed; r3d_phonon_final *finals; };
+
+struct Phonon {
+  double time, pathlen, recent, aexp;
+  v3 loc, dir, s1;
+  uint32_t moves, cell;
+  int type;
+};
+
+// ---- per-thread tallies (dataout.cpp:591-617), flushed once per CTA into its own row.  32-bit per thread (a thread
+// sees a few thousand phonons per launch), 64-bit from the CTA's row onwards. ----------------------------------
+struct Tally {
+  uint32_t v[R3D_NCOUNTERS];
+  R3D_DEV void clear() {
+#pragma unroll
+    for (int i = 0; i < R3D_NCOUNTERS; i++) v[i] = 0;
+  }
+  R3D_DEV void died(uint32_t fate) {
+    const uint32_t f = fate & 0xFF;
+    v[R3D_CNT_LOST] += (f == R3D_FATE_LOST);
+    v[R3D_CNT_TIMEOUT] += (f == R3D_FATE_TIMEOUT);
+    v[R3D_CNT_INVALID] += (f == R3D_FATE_INVALID);
+    if (f == R3D_FATE_INVALID) v[7] |= (fate >> 8);
+  }
+  // all threads of the CTA must call this
+  R3D_DEV void flush(unsigned long long *row, unsigned long long (*sm)[R3D_NCOUNTERS]) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < R3D_NCOUNTERS; k++) {
+      unsigned long long x = v[k];
+      if (k == 7) { for (int o = 16; o > 0; o >>= 1) x |= __shfl_down_sync(R3D_FULL, x, o); }
+      else { for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(R3D_FULL, x, o); }
+      if (lane == 0) sm[warp][k] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < R3D_NCOUNTERS) {
+      unsigned long long x = 0;
+      for (unsigned w = 0; w < nw; w++) { if (threadIdx.x == 7) x |= sm[w][threadIdx.x]; else x += sm[w][threadIdx.x]; }
+      if (x) { if (threadIdx.x == 7) row[threadIdx.x] |= x; else row[threadIdx.x] += x; }
+    }
+  }
+};
+
+// ---- the slots (phonons.hpp:69-126): struct of arrays in shared memory, 16-byte elements where fields travel
+// together.  Every accessor derives its address from the CTA's dynamic shared-memory symbol, so the compiler emits
+// LDS / STS (pointers kept in a struct were treated as generic and cost a long-scoreboard wait per access).
+#define R3D_SLOT_BYTES 144u
+#define R3D_SLOT_BYTES_TRACE 156u
+extern __shared__ __align__(16) unsigned char r3d_smem[];
+template <bool TRACE>
+struct Slots {
+  uint32_t S, cell_doubles;
+  R3D_DEV double2 &tp(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem)[s]; }                     // (time alive, path length)
+  R3D_DEV double2 &ra(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 16)[s]; }    // (recent travel time, attenuation exponent)
+  R3D_DEV double2 &lxy(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 32)[s]; }   // location x, y
+  R3D_DEV double2 &lzdz(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 48)[s]; }  // location z, direction z
+  R3D_DEV double2 &dxy(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 64)[s]; }   // direction x, y (unit direction of travel, e3)
+  R3D_DEV double2 &sxy(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 80)[s]; }   // polarisation direction x, y (unit, s1; carried
+  R3D_DEV double &sz(uint32_t s) const { return reinterpret_cast<double *>(r3d_smem + (size_t)S * 112)[s]; }     //  for P phonons too, like mPol, phonons.hpp:109-118)
+  R3D_DEV uint4 &meta(uint32_t s) const { return reinterpret_cast<uint4 *>(r3d_smem + (size_t)S * 96)[s]; }      // (move count, cell, draw ordinal, ray type)
+  R3D_DEV unsigned long long &idx(uint32_t s) const { return reinterpret_cast<unsigned long long *>(r3d_smem + (size_t)S * 120)[s]; }   // global phonon index
+  // the queued request: draw {31-bit draw, table | kind}; face {draw for the S-polarisation choice, draw for the
+  // outcome choice}, exit face id in the two top bits
+  R3D_DEV uint2 &req(uint32_t s) const { return reinterpret_cast<uint2 *>(r3d_smem + (size_t)S * 128)[s]; }
+  R3D_DEV double *cells() const { return reinterpret_cast<double *>(r3d_smem + (size_t)S * 136); }               // staged cell parameters
+  // trace mode only: [3][S] catches, scatters, iterations
+  R3D_DEV uint32_t &tr(int which, uint32_t s) const { return reinterpret_cast<uint32_t *>(r3d_smem + (size_t)S * 136 + (size_t)cell_doubles * 8)[(uint32_t)which * S + s]; }
+  // queues of slot indices: buffer 0 / 1 = [cur|next] ready-to-advance slots from the front, free slots from the back;
+  // buffer 2 = table draws: scatter draws from the front, source draws from the back; buffer 3 = face events: P from
+  // the front, S from the back
+  R3D_DEV uint16_t *queue(uint32_t buf) const {
+    return reinterpret_cast<uint16_t *>(r3d_smem + (size_t)S * (TRACE ? 148 : 136) + (size_t)cell_doubles * 8) + (size_t)buf * S;
+  }
+};
+
+// counters of the queues: cnt[0..3] = {advance, free} x {buffer 0, buffer 1}; cnt[4..7] = scatter draws, source draws, P faces, S faces
+struct Ctl {
+  unsigned long long base;          // first phonon (relative to the job) granted to this CTA in this iteration
+  uint32_t granted, exhausted, done, cursor[2];
+  uint32_t cnt[8];
+  unsigned long long t_phase[2];    // clock cycles spent in phase 1 / phase 2 (thread 0's view)
+  uint32_t iterations;
+};
+enum { CNT_SCAT = 4, CNT_SRC, CNT_FP, CNT_FS };
+
+// A warp takes the next 32-entry chunk of the current phase's work list
+R3D_DEV uint32_t next_chunk(uint32_t *cursor) {
+  uint32_t c = 0;
+  if ((threadIdx.x & 31u) == 0) c = atomicAdd(cursor, 1u);
+  return __shfl_sync(R3D_FULL, c, 0);
+}
+
+template <bool TRACE>
+R3D_DEV void write_final(const Slots<TRACE> &A, const Job &J, uint32_t s, const Phonon &p, uint32_t fate, uint32_t ordinal) {
+  if (!TRACE) return;
+  r3d_phonon_final *f = J.finals + (A.idx(s) - J.first);
+  f->time = p.time; f->pathlen = p.pathlen; f->amp = exp(-p.aexp);
+  f->loc[0] = p.loc.x; f->loc[1] = p.loc.y; f->loc[2] = p.loc.z;
+  angles_of(p.dir, f->theta, f->phi);
+  f->pol = pol_angle_of(p.dir, p.s1);
+  f->moves = p.moves; f->cell = p.cell; f->type = (uint32_t)p.type; f->fate = fate;
+  f->draws = ordinal; f->catches = A.tr(0, s); f->scatters = A.tr(1, s); f->iters = A.tr(2, s);
+}
+
+// one 32-byte take-off-angle record through the read-only path (two 16-byte loads of the same sector)
+R3D_DEV double4 load_toa(const double4 *p) {
+  const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// CellFace::VelocityJump (media_cellface.cpp:83-99).  Equal velocities give exactly 0 in the reference too
+// (2*(0)/(v+v)); testing for that first keeps 0/x off the slow path of the FP64 division.
+template <class Cell>
+R3D_DEV double velocity_jump(const DevModel &M, const double *cells, uint32_t cell, uint32_t other, v3 loc) {
+  const double *c = cells + (size_t)cell * M.cell_nparam, *o = cells + (size_t)other * M.cell_nparam;
+  double v1 = Cell::veloc(c, 0, loc), v2 = Cell::veloc(o, 0, loc);
+  double dvp = (v1 == v2 && v1 > 0.0) ? 0.0 : fabs(2 * (v2 - v1) / (v2 + v1));
+  v1 = Cell::veloc(c, 1, loc); v2 = Cell::veloc(o, 1, loc);
+  double dvs = (v1 == v2 && v1 > 0.0) ? 0.0 : fabs(2 * (v2 - v1) / (v2 + v1));
+  return (dvp > dvs) ? dvp : dvs;
+}
+
+// What happens at a face (phonons.cpp:629-676), decided where the phonon arrives so that the draws the face
+// event will consume can be taken from the stream in order.
+enum { FACE_NONE = 0, FACE_LOST, FACE_CONTINUOUS, FACE_BEND, FACE_FULLRT };
+template <class Cell>
+R3D_DEV int face_action(const DevModel &M, const double *cells, uint32_t fl, uint32_t cell, uint32_t other, v3 loc) {
+  if (fl & R3D_FACE_REFLECT) return FACE_FULLRT;                                    // phonons.cpp:640-646
+  if (fl & R3D_FACE_ADJOIN) {                                                       // Phonon::Refract, phonons.cpp:225-255
+    if (fl & R3D_FACE_DISCON) return FACE_FULLRT;
+    return (velocity_jump<Cell>(M, cells, cell, other, loc) > 0.00001) ? FACE_BEND : FACE_CONTINUOUS;
+  }
+  return FACE_LOST;                                                                 // phonons.cpp:675
+}
+
+// Phonon::Refraction_FullRT (phonons.cpp:429-476) + CellFace::GetRTBasis (media_cellface.cpp:122-149)
+template <class Cell>
+R3D_DEV void refraction_fullrt(const DevModel &M, const double *cells, Phonon &p, int face, bool adjoin, uint32_t other,
+                               uint32_t k_spol, uint32_t k_choose) {
+  const double *c = cells + (size_t)p.cell * M.cell_nparam;
+  RTCoef rt;
+  rt.init(Cell::normal(c, face, p.loc), p.dir);
+  rt.densR = Cell::dens(c, p.loc);
+  rt.velR[0] = Cell::veloc(c, 0, p.loc);
+  rt.velR[1] = Cell::veloc(c, 1, p.loc);
+  if (adjoin) {
+    const double *o = cells + (size_t)other * M.cell_nparam;
+    rt.densT = Cell::dens(o, p.loc);
+    rt.velT[0] = Cell::veloc(o, 0, p.loc);
+    rt.velT[1] = Cell::veloc(o, 1, p.loc);
+  } else {                                    // free surface
+    rt.densT = 0.0; rt.velT[0] = 1e-12; rt.velT[1] = 1e-12; rt.notransmit = true;
+  }
+  int intype = R3D_RAY_P;
+  if (p.type == R3D_RAY_S) intype = rt.choose_spol(p.s1, k_spol);          // DirectionOfMotion() of an S phonon is s1
+  rt.get_coefs(intype);
+  rt.choose(k_choose);
+  const bool reflected = (rt.choice == R_P || rt.choice == R_SV || rt.choice == R_SH);
+  const v3 outdir = unit_else(rt.chosen_ray_dir(), V(0, 0, 1));          // mDir.Set(outdir.Theta(), outdir.Phi())
+  p.type = (rt.choice == R_P || rt.choice == T_P) ? R3D_RAY_P : R3D_RAY_S;
+  if (p.type == R3D_RAY_S) p.s1 = pol_from_pdom(outdir, rt.chosen_pdom());  // phonons.cpp:459-465
+  else p.s1 = carry_pol(p.dir, p.s1, outdir);                                 // mPol is left as it was
+  p.dir = outdir;
+  if (!reflected) p.cell = other;
+}
+
+// Phonon::Refraction_Bend (phonons.cpp:311-405)
+template <class Cell>
+R3D_DEV void refraction_bend(const DevModel &M, const double *cells, Phonon &p, int face, uint32_t other) {
+  const double *c = cells + (size_t)p.cell * M.cell_nparam;
+  const double *o = cells + (size_t)other * M.cell_nparam;
+  const v3 mdir = p.dir;
+  const v3 fnorm = Cell::normal(c, face, p.loc);
+  const v3 fpara = inplane_unit_perp(fnorm, mdir);
+  const v3 fparash = cross(fnorm, fpara);
+  const double veli = Cell::veloc(c, p.type, p.loc), velo = Cell::veloc(o, p.type, p.loc);
+  const double sini = dot(fpara, mdir);
+  double sino = (velo / veli) * sini;
+  bool transfer; double coso;
+  if (sino >= 1.0) { transfer = false; sino = sini; coso = -1.0 * dot(fnorm, mdir); }
+  else { transfer = true; coso = sqrt(1.0 - (sino * sino)); }
+  const v3 outraw = add(scal(fpara, sino), scal(fnorm, coso));
+  const v3 outdir = unit_else(outraw, V(0, 0, 1));
+  if (p.type != R3D_RAY_P) {
+    const v3 svbasei = cross(fparash, mdir), svbaseo = cross(fparash, outraw);
+    const double shcomi = dot(p.s1, fparash), svcomi = dot(p.s1, svbasei);
+    p.s1 = pol_from_pdom(outdir, add(scal(fparash, shcomi), scal(svbaseo, svcomi)));
+  } else {
+    p.s1 = hats(outdir).th;                     // polout = 0 for P (phonons.cpp:366, 393)
+  }
+  p.dir = outdir;
+  if (transfer) p.cell = other;
+}
+
+// kinds of follow-up work a slot can be queued for
+enum { OUT_NONE = -1, OUT_ADV = 0, OUT_FREE, OUT_SCAT, OUT_SRC, OUT_FP, OUT_FS };
+
+// Append this lane's slot to the queue of its follow-up kind: lanes of one kind find each other with one match.any,
+// their leader reserves room with one shared-memory atomic.  All lanes of the warp call this.
+template <bool TRACE>
+R3D_DEV void route(const Slots<TRACE> &A, Ctl &C, int nxt, int out, uint32_t s) {
+  const unsigned peers = __match_any_sync(R3D_FULL, out);
+  if (out < 0) return;
+  const unsigned lane = threadIdx.x & 31u;
+  const int leader = __ffs(peers) - 1;
+  const uint32_t ci = (out < 2) ? (uint32_t)(nxt * 2 + out) : (uint32_t)(2 + out);
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(&C.cnt[ci], (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  const uint32_t j = base + __popc(peers & ((1u << lane) - 1u));
+  const uint32_t buf = (out < 2) ? (uint32_t)nxt : 1u + ((uint32_t)out >> 1);
+  A.queue(buf)[(out & 1) ? A.S - 1u - j : j] = (uint16_t)s;
+}
+
+// =====================================================================================================
+// phase 1a: one Propagate-loop iteration up to the event's classification (phonons.cpp:542-623)
+// =====================================================================================================
+template <class Cell, bool TRACE>
+R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, const double *cells, uint32_t s, Tally &T) {
+  Phonon p;
+  const double2 tp = A.tp(s), ra = A.ra(s), lxy = A.lxy(s), lzdz = A.lzdz(s), dxy = A.dxy(s);
+  const uint4 meta = A.meta(s);
+  p.time = tp.x; p.pathlen = tp.y; p.recent = ra.x; p.aexp = ra.y;
+  p.loc = V(lxy.x, lxy.y, lzdz.x);
+  p.dir = V(dxy.x, dxy.y, lzdz.y);
+  p.moves = meta.x; p.cell = meta.y; p.type = (int)meta.w;
+  uint32_t ordinal = meta.z;
+  T.v[R3D_CNT_EVENTS]++;
+  if (TRACE) A.tr(2, s)++;
+  uint32_t fate = 0;
+  int out = OUT_ADV;
+  if (p.time > M.ttl) fate = R3D_FATE_TIMEOUT;                  // phonons.cpp:549-552
+  else if ((p.moves % 128u) == 127u) {                          // phonons.cpp:554-584
+    int why = -1;
+    if (isnan(p.pathlen)) why = R3D_INV_PATH_NAN;
+    else if (isnan(p.time)) why = R3D_INV_TIME_NAN;
+    else if (p.pathlen < 0) why = R3D_INV_PATH_NEGATIVE;
+    else if ((p.time < 0) || (p.recent < 0)) why = R3D_INV_TIME_NEGATIVE;
+    else if (p.recent == 0) why = R3D_INV_STUCK;
+    else if (p.recent < M.slow_concern) why = R3D_INV_SLOW;
+    else if (p.moves > M.loop_concern) why = R3D_INV_LOOP_EXCEED;
+    if (why >= 0) fate = R3D_FATE_INVALID | ((1u << why) << 8);
+    else p.recent = 0;
+  }
+  bool dir_changed = false, s1_loaded = false;
+  if (!fate) {
+    const double *c = cells + (size_t)p.cell * M.cell_nparam;
+    typename Cell::Path P;
+    const double edgelen = Cell::path(M, c, p.type, p.loc, p.dir, P);
+    if (edgelen == pinf()) fate = R3D_FATE_TIMEOUT;             // phonons.cpp:595-598
+    else {
+      // the event's draws: path length first, then at most two more, all from Philox block ordinal/4 (and the next
+      // one when they run over its end)
+      Rng g; g.init(J.seed, A.idx(s));
+      const uint32_t o = ordinal & 3u, b = ordinal >> 2;
+      g.block(b);
+      const uint32_t w1 = g.w[1], w2 = g.w[2], w3 = g.w[3];
+      const uint32_t k_path = ((o == 0) ? g.w[0] : (o == 1) ? w1 : (o == 2) ? w2 : w3) >> 1;
+      const uint32_t scat = __ldg(M.cell_scat + p.cell);
+      // Scatterer::GetRandomPathLength (scatterers.cpp:297-307)
+      const double r = 1.0 - ((double)k_path) / (kRandMax + 1);
+      const double scatlen = -log(r) * __ldg(M.scat_mfp + scat * 2 + p.type);
+      const bool scatter = scatlen < edgelen;
+      const Travel tr = Cell::advance(M, c, p.type, scatter ? scatlen : edgelen, p.loc, p.dir, P);
+      // Phonon::Move (phonons.cpp:62-70)
+      p.pathlen += tr.len; p.time += tr.time; p.recent += tr.time;
+      p.loc = tr.loc; p.aexp += tr.aexp; p.moves += 1;
+      if (Cell::curved) {            // the ray turned: the polarisation ANGLE is what the reference carries along
+        const double2 sxy = A.sxy(s);
+        p.s1 = carry_pol(p.dir, V(sxy.x, sxy.y, A.sz(s)), tr.dir);
+        p.dir = tr.dir;
+        dir_changed = true; s1_loaded = true;
+      }
+      // what follows, and how many more draws it takes
+      uint32_t more = 0, fl = 0, other = 0;
+      int action = FACE_NONE;
+      if (scatter) {
+        if (!M.no_deflect) more = 2;                              // conversion type, take-off angle (scatterers.cpp:332,336)
+      } else {
+        const uint32_t fi = p.cell * M.faces_per_cell + P.face;
+        fl = __ldg(M.face_flags + fi);
+        other = __ldg(M.face_other + fi);
+        action = face_action<Cell>(M, cells, fl, p.cell, other, p.loc);
+        if (action == FACE_FULLRT) more = (p.type == R3D_RAY_S) ? 2 : 1;   // [S polarisation choice,] outcome choice
+      }
+      uint32_t k1 = 0, k2 = 0;
+      if (more) {
+        uint32_t x0 = 0, x1 = 0;
+        if (o + more > 3u) { g.block(b + 1); x0 = g.w[0]; x1 = g.w[1]; }
+        const uint32_t i1 = o + 1, i2 = o + 2;
+        k1 = ((i1 == 1) ? w1 : (i1 == 2) ? w2 : (i1 == 3) ? w3 : x0) >> 1;
+        k2 = ((i2 == 2) ? w2 : (i2 == 3) ? w3 : (i2 == 4) ? x0 : x1) >> 1;
+      }
+      ordinal += 1 + more;
+      if (scatter) {
+        // Scatterer::GetRandomScatteredRelativePhonon (scatterers.cpp:318-363); the table draw is queued
+        if (M.no_deflect) {
+          if (!s1_loaded) { const double2 sxy = A.sxy(s); p.s1 = V(sxy.x, sxy.y, A.sz(s)); s1_loaded = true; }
+          double st, ct;
+          sincos(M.min_theta, &st, &ct);                          // Phonon(ThetaPhi(0,0)) nudged to min_theta, pol 0
+          transform(p.dir, p.s1, st, ct, 0.0, 1.0, 0.0, 1.0);
+          dir_changed = true;
+          T.v[R3D_CNT_SCATTERS]++;
+          if (TRACE) A.tr(1, s)++;
+        } else {
+          const uint32_t conv = cdf_search_small(M.scat_whole + (scat * 2 + p.type) * 4, 4, k1);
+          A.req(s) = make_uint2(k2, scat * 4 + conv);
+          out = OUT_SCAT;
+        }
+      } else if (action == FACE_LOST && !(fl & R3D_FACE_COLLECT)) fate = R3D_FATE_LOST;
+      else if (action == FACE_CONTINUOUS && !(fl & R3D_FACE_COLLECT)) p.cell = other;   // Refraction_Continuous
+      else {
+        // collection and / or R/T and / or bending: phase 2.  For P only the outcome draw exists (k1).
+        const uint32_t ka = (p.type == R3D_RAY_S) ? k1 : 0u, kb = (p.type == R3D_RAY_S) ? k2 : k1;
+        A.req(s) = make_uint2(ka | ((uint32_t)(P.face & 1) << 31), kb | ((uint32_t)(P.face >> 1) << 31));
+        out = (p.type == R3D_RAY_P) ? OUT_FP : OUT_FS;
+      }
+    }
+  }
+  if (fate) {
+    T.died(fate);
+    if (TRACE) {
+      if (!s1_loaded) { const double2 sxy = A.sxy(s); p.s1 = V(sxy.x, sxy.y, A.sz(s)); }
+      write_final<TRACE>(A, J, s, p, fate, ordinal);
+    }
+    return OUT_FREE;
+  }
+  A.tp(s) = make_double2(p.time, p.pathlen);
+  A.ra(s) = make_double2(p.recent, p.aexp);
+  A.lxy(s) = make_double2(p.loc.x, p.loc.y);
+  A.lzdz(s) = make_double2(p.loc.z, p.dir.z);
+  if (dir_changed) {
+    A.dxy(s) = make_double2(p.dir.x, p.dir.y);
+    A.sxy(s) = make_double2(p.s1.x, p.s1.y);
+    A.sz(s) = p.s1.z;
+  }
+  A.meta(s) = make_uint4(p.moves, p.cell, ordinal, (uint32_t)p.type);
+  return out;
+}
+
+// phase 1b: a free slot takes the next phonon: ShearDislocation::GenerateEventPhonon (events.cpp:111-124) ->
+// PhononSource::GenerateRandomPhonon (sources.cpp:156-170) -> Phonon ctor (phonons.hpp:193-207)
+template <bool TRACE>
+R3D_DEV void refill_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, uint32_t s, unsigned long long rel, Tally &T) {
+  const unsigned long long idx = J.first + rel;
+  Rng g; g.init(J.seed, idx);
+  g.block(0);
+  const uint32_t rt3 = cdf_search_small(M.src_whole, 3, g.w[0] >> 1);
+  A.req(s) = make_uint2(g.w[1] >> 1, rt3);                    // the take-off angle is drawn in phase 2
+  A.tp(s) = make_double2(0.0, 0.0);
+  A.ra(s) = make_double2(0.0, 0.0);
+  A.lxy(s) = make_double2(M.src_loc[0], M.src_loc[1]);
+  A.lzdz(s) = make_double2(M.src_loc[2], 0.0);
+  A.idx(s) = idx;
+  A.meta(s) = make_uint4(0u, M.src_cell, 2u, (rt3 == R3D_RAY_P) ? R3D_RAY_P : R3D_RAY_S);
+  if (TRACE) { A.tr(0, s) = 0; A.tr(1, s) = 0; A.tr(2, s) = 0; }
+  T.v[6]++;
+}
+
+// =====================================================================================================
+// phase 2a: ProbDist::GetRandomIndex on the queued table + take-off angle, then either the new phonon's
+// direction (sources.cpp:156-170) or Phonon::Transform (phonons.cpp:116-170)
+// =====================================================================================================
+template <bool TRACE>
+R3D_DEV void draw_one(const DevModel &M, const Slots<TRACE> &A, uint32_t s, bool is_src, Tally &T) {
+  const uint2 q = A.req(s);
+  if (is_src) {
+    // new phonon: direction = the drawn take-off angle, polarisation angle pi/2 for SH else 0 (phonons.hpp:193-207)
+    const uint32_t ti = cdf_search(M.src_cdf + (size_t)q.y * M.n_toa, M.n_toa, M.src_guide + (size_t)q.y * M.guide_stride, M.guide_shift, q.x);
+    const double4 t = load_toa(M.toa + ti);                   // sin th, cos th, sin ph, cos ph
+    A.dxy(s) = make_double2(t.x * t.w, t.x * t.z);
+    A.lzdz(s).y = t.y;
+    if (q.y == R3D_RAY_SH) { A.sxy(s) = make_double2(-t.z, t.w); A.sz(s) = 0.0; }                 // phi-hat
+    else { A.sxy(s) = make_double2(t.y * t.w, t.y * t.z); A.sz(s) = -t.x; }                       // theta-hat
+  } else {
+    const uint32_t ti = cdf_search(M.scat_cdf + (size_t)q.y * M.n_toa, M.n_toa, M.scat_guide + (size_t)q.y * M.guide_stride, M.guide_shift, q.x);
+    const double4 t = load_toa(M.toa + ti);
+    const uint32_t conv = q.y & 3u;
+    double2 rp = make_double2(1.0, 0.0);                        // (cos, sin) of the relative polarisation angle
+    if (conv == 3u) rp = __ldg(M.scat_spol + (size_t)(q.y >> 2) * M.n_toa + ti);
+    const double2 dxy = A.dxy(s), sxy = A.sxy(s);
+    v3 e3 = V(dxy.x, dxy.y, A.lzdz(s).y), s1 = V(sxy.x, sxy.y, A.sz(s));
+    transform(e3, s1, t.x, t.y, t.z, t.w, rp.y, rp.x);
+    A.dxy(s) = make_double2(e3.x, e3.y);
+    A.lzdz(s).y = e3.z;
+    A.sxy(s) = make_double2(s1.x, s1.y);
+    A.sz(s) = s1.z;
+    A.meta(s).w = conv & 1u;                                  // PP,PS,SP,SS -> P,S,P,S
+    T.v[R3D_CNT_SCATTERS]++;
+    if (TRACE) A.tr(1, s)++;
+  }
+}
+
+// =====================================================================================================
+// phase 2b: everything that happens at a face that is not a plain hand-over: collection (dataout.cpp:545-568,
+// 103-216), free-surface / discontinuity R/T (phonons.cpp:429-476), Snell bending (phonons.cpp:311-405)
+// =====================================================================================================
+template <class Cell, bool TRACE>
+R3D_DEV int face_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, const double *cells, uint32_t s, Tally &T) {
+  Phonon p;
+  const double2 tp = A.tp(s), ra = A.ra(s), lxy = A.lxy(s), lzdz = A.lzdz(s), dxy = A.dxy(s), sxy = A.sxy(s);
+  const uint4 meta = A.meta(s);
+  const uint2 q = A.req(s);
+  p.time = tp.x; p.pathlen = tp.y; p.recent = ra.x; p.aexp = ra.y;
+  p.loc = V(lxy.x, lxy.y, lzdz.x);
+  p.dir = V(dxy.x, dxy.y, lzdz.y);
+  p.s1 = V(sxy.x, sxy.y, A.sz(s));
+  p.moves = meta.x; p.cell = meta.y; p.type = (int)meta.w;
+  const int face = (int)((q.x >> 31) | ((q.y >> 31) << 1));
+  const uint32_t k_spol = q.x & 0x7fffffffu, k_choose = q.y & 0x7fffffffu;
+  const uint32_t fi = p.cell * M.faces_per_cell + face;
+  const uint32_t fl = __ldg(M.face_flags + fi), other = __ldg(M.face_other + fi);
+
+  // ---- collection (dataout.cpp:545-568): every seismometer is pass-through (dataout.cpp:50), so all that contain
+  // the point must bin it.  Candidates come from the uniform grid over the seismometers' bounding spheres. --------
+  if ((fl & R3D_FACE_COLLECT) && M.n_seis > 0) {
+    const int cx_ = grid_axis_cell(p.loc.x, M.grid_min[0], M.grid_inv_h[0]);
+    const int cy_ = grid_axis_cell(p.loc.y, M.grid_min[1], M.grid_inv_h[1]);
+    const int cz_ = grid_axis_cell(p.loc.z, M.grid_min[2], M.grid_inv_h[2]);
+    if (cx_ >= 0 && cy_ >= 0 && cz_ >= 0 && cx_ < (int)M.grid_dim[0] && cy_ < (int)M.grid_dim[1] && cz_ < (int)M.grid_dim[2]) {
+      const uint32_t gcell = ((uint32_t)cz_ * M.grid_dim[1] + (uint32_t)cy_) * M.grid_dim[0] + (uint32_t)cx_;
+      const uint32_t i0 = __ldg(M.grid_start + gcell), i1 = __ldg(M.grid_start + gcell + 1);
+      uint32_t my_catches = 0;
+      for (uint32_t j = i0; j < i1; j++) {
+        const uint32_t k2 = __ldg(M.grid_items + j);
+        const double2 qa = __ldg(reinterpret_cast<const double2 *>(M.seis_sphere + k2));
+        const double2 qb = __ldg(reinterpret_cast<const double2 *>(M.seis_sphere + k2) + 1);
+        const double ddx = qa.x - p.loc.x, ddy = qa.y - p.loc.y, ddz = qb.x - p.loc.z;
+        if (ddx * ddx + ddy * ddy + ddz * ddz > qb.y) continue;   // cannot be within the gather radius
+        // rare from here on (a few per cent of the surface hits): the exact CatchPhonon test
+        const double vel = Cell::veloc(cells + (size_t)p.cell * M.cell_nparam, p.type, p.loc);
+        const v3 dopm = (p.type == R3D_RAY_P) ? p.dir : p.s1;   // Phonon::DirectionOfMotion (phonons.cpp:201-211)
+        uint32_t bin; double e[4];
+        if (seis_catch(M.seis + (size_t)k2 * R3D_SEIS_NPARAM, M.bin_dt, M.n_bins, p.time, p.loc, p.dir, dopm, p.type, exp(-p.aexp), vel, bin, e)) {
+          const size_t bb = (size_t)k2 * M.n_bins + bin;
+          atomicAdd(M.energies + bb * 5 + 0, e[0]);
+          atomicAdd(M.energies + bb * 5 + 1, e[1]);
+          atomicAdd(M.energies + bb * 5 + 2, e[2]);
+          atomicAdd(M.energies + bb * 5 + 3 + p.type, e[3]);
+          atomicAdd(M.counts + bb * 2 + p.type, 1ull);
+          my_catches++;
+        }
+      }
+      T.v[R3D_CNT_CATCHES] += my_catches;
+      if (TRACE && my_catches) A.tr(0, s) += my_catches;
+    }
+  }
+
+  // ---- reflection / refraction (phonons.cpp:640-676) ---------------------------------------------------
+  const int action = face_action<Cell>(M, cells, fl, p.cell, other, p.loc);
+  if (action == FACE_FULLRT) refraction_fullrt<Cell>(M, cells, p, face, (fl & R3D_FACE_ADJOIN) != 0, other, k_spol, k_choose);
+  else if (action == FACE_BEND) refraction_bend<Cell>(M, cells, p, face, other);
+  else if (action == FACE_CONTINUOUS) p.cell = other;
+  else {
+    T.died(R3D_FATE_LOST);
+    write_final<TRACE>(A, J, s, p, R3D_FATE_LOST, meta.z);
+    return OUT_FREE;
+  }
+  A.dxy(s) = make_double2(p.dir.x, p.dir.y);
+  A.lzdz(s).y = p.dir.z;
+  A.sxy(s) = make_double2(p.s1.x, p.s1.y);
+  A.sz(s) = p.s1.z;
+  A.meta(s) = make_uint4(meta.x, p.cell, meta.z, (uint32_t)p.type);
+  return OUT_ADV;
+}
+
+// =====================================================================================================
+// the kernel: persistent CTAs, S slots each
+// =====================================================================================================
+template <class Cell, bool TRACE>
+__global__ void __launch_bounds__(R3D_NT, R3D_MINBLOCKS)
+propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t cell_doubles, unsigned long long *block_tally,
+                 unsigned long long *block_clock) {
+  __shared__ unsigned long long tally_sm[R3D_NT / 32][R3D_NCOUNTERS];
+  __shared__ Ctl C;
+  Slots<TRACE> A; A.S = S; A.cell_doubles = cell_doubles;
+  const double *__restrict__ cells = M.cell_params;      // a few hundred bytes (layered models) to 0.7 MB (tetrahedra): L1 / L2 resident
+  for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) A.queue(0)[S - 1u - i] = (uint16_t)i;     // every slot starts free
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) C.cnt[k] = 0;
+    C.cnt[OUT_FREE] = S;
+    C.exhausted = 0; C.done = 0; C.t_phase[0] = 0; C.t_phase[1] = 0; C.iterations = 0;
+  }
+  const unsigned lane = threadIdx.x & 31u;
+  Tally T; T.clear();
+  int cur = 0;
+  long long t0 = 0;
+  __syncthreads();
+
+  for (;;) {
+    const int nxt = cur ^ 1;
+    // ---- grant new phonons to the free slots: one atomic on the job's work counter per CTA per iteration ------
+    if (threadIdx.x == 0) {
+      const uint32_t nf = C.cnt[cur * 2 + OUT_FREE];
+      uint32_t grant = 0;
+      if (nf && !C.exhausted) {
+        const unsigned long long b = atomicAdd(M.next_phonon, (unsigned long long)nf);
+        if (b < J.n) { const unsigned long long left = J.n - b; grant = (left < nf) ? (uint32_t)left : nf; C.base = b; }
+        if (grant < nf) C.exhausted = 1;
+      }
+      C.granted = grant;
+      C.cnt[nxt * 2 + OUT_ADV] = 0; C.cnt[nxt * 2 + OUT_FREE] = 0;
+      C.cnt[CNT_SCAT] = 0; C.cnt[CNT_SRC] = 0; C.cnt[CNT_FP] = 0; C.cnt[CNT_FS] = 0;
+      C.cursor[0] = 0; C.cursor[1] = 0;
+      C.done = (C.cnt[cur * 2 + OUT_ADV] == 0 && grant == 0);
+      t0 = clock64();
+    }
+    __syncthreads();
+    if (C.done) break;
+
+    // ---- phase 1: advance chunks, then refill chunks ---------------------------------------------------------
+    {
+      const uint32_t nA = C.cnt[cur * 2 + OUT_ADV], nR = C.granted;
+      const uint32_t cA = (nA + 31u) >> 5, cR = (nR + 31u) >> 5;
+      const uint16_t *q = A.queue((uint32_t)cur);
+      const unsigned long long base = C.base;
+      for (;;) {
+        const uint32_t c = next_chunk(&C.cursor[0]);
+        if (c >= cA + cR) break;
+        int out = OUT_NONE;
+        uint32_t s = 0;
+        if (c < cA) {
+          const uint32_t j = c * 32u + lane;
+          if (j < nA) { s = q[j]; out = advance_one<Cell, TRACE>(M, J, A, cells, s, T); }
+        } else {
+          const uint32_t j = (c - cA) * 32u + lane;
+          if (j < nR) { s = q[S - 1u - j]; refill_one<TRACE>(M, J, A, s, base + j, T); out = OUT_SRC; }
+        }
+        route<TRACE>(A, C, nxt, out, s);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { const long long t1 = clock64(); C.t_phase[0] += (unsigned long long)(t1 - t0); t0 = t1; }
+
+    // ---- phase 2: face chunks (S, then P), then draw chunks (scatter, then source) -----------------------------
+    {
+      const uint32_t nFS = C.cnt[CNT_FS], nFP = C.cnt[CNT_FP], nDS = C.cnt[CNT_SCAT], nDR = C.cnt[CNT_SRC];
+      const uint32_t c0 = (nFS + 31u) >> 5, c1 = c0 + ((nFP + 31u) >> 5), c2 = c1 + ((nDS + 31u) >> 5), c3 = c2 + ((nDR + 31u) >> 5);
+      const uint16_t *qd = A.queue(2), *qf = A.queue(3);
+      for (;;) {
+        const uint32_t c = next_chunk(&C.cursor[1]);
+        if (c >= c3) break;
+        int out = OUT_NONE;
+        uint32_t s = 0;
+        if (c < c0) {
+          const uint32_t j = c * 32u + lane;
+          if (j < nFS) { s = qf[S - 1u - j]; out = face_one<Cell, TRACE>(M, J, A, cells, s, T); }
+        } else if (c < c1) {
+          const uint32_t j = (c - c0) * 32u + lane;
+          if (j < nFP) { s = qf[j]; out = face_one<Cell, TRACE>(M, J, A, cells, s, T); }
+        } else if (c < c2) {
+          const uint32_t j = (c - c1) * 32u + lane;
+          if (j < nDS) { s = qd[j]; draw_one<TRACE>(M, A, s, false, T); out = OUT_ADV; }
+        } else {
+          const uint32_t j = (c - c2) * 32u + lane;
+          if (j < nDR) { s = qd[S - 1u - j]; draw_one<TRACE>(M, A, s, true, T); out = OUT_ADV; }
+        }
+        route<TRACE>(A, C, nxt, out, s);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { C.t_phase[1] += (unsigned long long)(clock64() - t0); C.iterations++; }
+    cur = nxt;
+  }
+  T.flush(block_tally + (size_t)blockIdx.x * R3D_NCOUNTERS, tally_sm);
+  if (threadIdx.x == 0) {
+    block_clock[3 * blockIdx.x + 0] += C.t_phase[0];
+    block_clock[3 * blockIdx.x + 1] += C.t_phase[1];
+    block_clock[3 * blockIdx.x + 2] += C.iterations;
+  }
+}
+
+}  // namespace r3d

@@ -30,12 +30,14 @@ with tempfile.TemporaryDirectory() as tmp:
     cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
     sass = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
 
-lines, cur, grab = [], None, False
+# every function whose symbol contains `sym`; keep the one whose instruction count equals the report's
+cands, lines, cur, grab = [], [], None, False
 for l in sass.splitlines():
     if l.startswith("//--------------------- .text."):
-        grab = sym in l and "_ZN" in l
         if grab and lines:
-            break                       # first matching function only
+            cands.append(lines)
+        grab = sym in l and "_ZN" in l
+        lines, cur = [], None
         continue
     if not grab:
         continue
@@ -45,6 +47,9 @@ for l in sass.splitlines():
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", l):
         lines.append(cur)
+if grab and lines:
+    cands.append(lines)
+lines = min(cands, key=lambda c: abs(len(c) - len(inst))) if cands else []
 if len(lines) != len(inst):
     print(f"warning: {len(lines)} instructions in the cubin vs {len(inst)} in the report; attribution may be shifted", file=sys.stderr)
 agg = collections.defaultdict(lambda: [0, 0, 0, 0])
@@ -67,3 +72,10 @@ print(f"{'file:line':28s} {'warp-inst%':>10s} {'lanes':>6s} {'stall%':>7s}  sour
 for where, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     name = f"{where[0]}:{where[1]}" if where else "?"
     print(f"{name:28s} {100 * a[0] / tot_i:10.2f} {a[1] / max(a[0], 1):6.1f} {100 * a[2] / max(tot_s, 1):7.2f}  {text(where)}")
+
+# optional: dump the SASS of one source line:  ... <top N> <file:line>
+if len(sys.argv) > 4:
+    f, n = sys.argv[4].split(":")
+    for (txt, ni, nt, ns), where in zip(inst, lines):
+        if where == (f, int(n)):
+            print(f"{ni:10d} {nt / max(ni, 1):5.1f} {ns:5d}  {txt}")

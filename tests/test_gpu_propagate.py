@@ -109,7 +109,7 @@ def test_empty_and_ragged_ranges():
         e, c, k = eng.fetch()
         assert int(k[abi.R3D_CNT_PHONONS]) == 130 and int(k[:3].sum()) == 130 and t >= 0
         assert eng.trace(0).size == 0
-        assert eng.launch_count >= 2 * 3
+        assert eng.launch_count >= 2 * 2 + 1      # one propagate launch per non-empty job + one tally reduction per job
 
 
 def test_no_deflect_and_no_seismometers():
