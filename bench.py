@@ -13,7 +13,7 @@ reference's own host code (integration/_build/r3d_gpu_main, see radiative3d_b200
            the single end-of-run NCCL all-reduce of the bins.
   e2e      the same batch through the C ABI with HOST buffers: r3d_create (H2D of the pinned model tables) +
            r3d_run + r3d_fetch (D2H of bins and counters) + r3d_destroy, wall clock.
-  roofline per-kernel CUDA-event times from a separate profiling step (r3d_set_profiling) for the dominant kernel.
+  roofline the propagate kernel (one launch per step and GPU) timed with CUDA events on its stream over one more step.
   cpu_baseline  the unmodified reference binary (oracle/_ref/r3d_ref_main) on one host core, bounded sample.
 
 --impl reference times the reference's own CPU implementation with all host threads it can use (independent
@@ -255,43 +255,45 @@ def main():
         raise SystemExit(f"bench.py: traced {int(counters[abi.R3D_CNT_PHONONS])} phonons, expected {total}")
     events_total = int(counters[abi.R3D_CNT_EVENTS])
 
-    # ---- roofline: per-kernel CUDA-event times of one extra step (rank 0 of any N; kernels are per GPU) -------
+    # ---- roofline of the propagate kernel (the only kernel of the path): CUDA events on its launching stream, live,
+    # over one extra step of the same size (rank 0's GPU; the kernels are per GPU)
     roofline = None
     eng.reset()
     eng.set_profiling(True)
     enqueue(W + K)
     eng.sync()
     kt = eng.kernel_times()
-    _, _, kc = eng.fetch()
+    kt["phonons"] = per
     eng.set_profiling(False)
     if rank == 0:
         bytes_draw = algorithmic_bytes_per_draw(model.n_toa)
-        state_rw = 102 + 92                       # advance kernel: pool bytes read + written per live phonon
-        alg = {"advance": kt["advance"][2] * state_rw,
-               "draw": kt["draw"][2] * bytes_draw,
-               "interface": kt["interface"][2] * 130 + int(kc[abi.R3D_CNT_CATCHES]) * BYTES_PER_CATCH}
-        tot_s = sum(v[0] for v in kt.values())
-        dom = max(kt, key=lambda k: kt[k][0])
+        alg = kt["draws"] * bytes_draw + kt["catches"] * BYTES_PER_CATCH
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None
+        traffic, traffic_note = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
-        except (OSError, ValueError):
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj["dram_bytes_per_phonon"] * kt["phonons"] / max(kt["launches"], 1) if "phonons" in kt else None
+            traffic_note = tj.get("source")
+        except (OSError, ValueError, KeyError):
             pass
-        sec, nl, units = kt[dom]
-        achieved = alg[dom] / sec / 1e9
-        roofline = {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                    "avg_launch_ms": 1e3 * sec / max(nl, 1), "algorithmic_bytes_per_launch": alg[dom] / max(nl, 1),
-                    "share_of_step": {k: v[0] / tot_s for k, v in kt.items()},
-                    "units": {k: v[2] for k, v in kt.items()},
-                    "step_algorithmic_GBps_survey8d": (kt["draw"][2] * bytes_draw + int(kc[abi.R3D_CNT_CATCHES]) * BYTES_PER_CATCH) / tot_s / 1e9}
+        sec, nl = kt["seconds"], max(kt["launches"], 1)
+        achieved = alg / sec / 1e9
+        ph = kt["phase1_seconds"] + kt["phase2_seconds"]
+        roofline = {"bound": "hbm", "kernel": "propagate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                    "avg_launch_ms": 1e3 * sec / nl, "algorithmic_bytes_per_launch": alg / nl,
+                    "algorithmic_bytes": f"{bytes_draw} B per table draw + {BYTES_PER_CATCH} B per bin update (SURVEY 8d)",
+                    "share_of_step": {"propagate_kernel": 1.0},
+                    "phase_share": {"advance+refill": kt["phase1_seconds"] / ph if ph else None,
+                                    "draw+face": kt["phase2_seconds"] / ph if ph else None},
+                    "units": {"phonons": per, "loop_events": kt["events"], "table_draws": kt["draws"], "bin_updates": kt["catches"]},
+                    "ctas": kt["ctas"], "iterations_of_busiest_cta": kt["iterations"]}
 
     # ---- e2e: host model in, host bins out, through the C ABI ---------------------------------------------------
     eng.close()
@@ -330,7 +332,7 @@ def main():
                                    f"TOA degree {TOA_DEGREE} ({model.n_toa} take-off angles, {h2d / 1e9:.2f} GB of tables)",
                        "phonons_per_gpu_per_step": per, "global_phonons_per_step": per * world, "parallelism": f"phonon-index sharding x{world}, "
                        "one NCCL all-reduce of the bins at the end",
-                       "cache": "inputs larger than L2: 0.42 GB of CDF tables + 0.27 GB phonon pool vs 126 MB L2",
+                       "cache": "inputs larger than L2: 0.42 GB of CDF tables + 0.06 GB of guide tables, gathered at random, vs 126 MB L2",
                        "timing": "CUDA events on the launching stream (r3d_sync) + torch events around the all-reduce, max over ranks",
                        "wall_ms_per_step": 1e3 * wall_s / K,
                        "loop_events_per_second": events_total / dev_s, "events_per_phonon": events_total / total,

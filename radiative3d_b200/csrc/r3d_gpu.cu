@@ -17,6 +17,7 @@
 #include <condition_variable>
 #include <deque>
 #include <stdlib.h>
+#include <chrono>
 #include "r3d_gpu.h"
 #include "r3d_device.cuh"
 #include "r3d_resident.cuh"
@@ -177,10 +178,10 @@ struct DevState {
   // launch geometry of the persistent kernel
   int grid = 0, threads = 0, blocks_per_sm = 1;
   size_t smem_block = 0;                   // dynamic shared memory available to one CTA
-  uint32_t cell_doubles = 0;               // cell parameters staged in shared memory (0: read from global memory)
+  uint32_t table_bytes = 0;                // small-model tables staged in shared memory (0: read through L1 / L2)
   uint32_t max_slots[2] = {0, 0};          // slots per CTA that fit [plain | trace]
   unsigned long long *block_tally = nullptr;   // [grid][R3D_NCOUNTERS], one row per CTA: no atomics
-  unsigned long long *block_clock = nullptr;   // [grid][3]: cycles in phase 1, cycles in phase 2, iterations
+  unsigned long long *block_clock = nullptr;   // [grid][R3D_NCLOCKS] (r3d_resident.cuh)
   // worker thread: launches queued jobs on this device's stream
   std::thread worker;
   std::mutex mu;
@@ -205,10 +206,12 @@ struct r3d_handle {
 
 namespace {
 
+// Device memory comes from the device's stream-ordered pool, whose release threshold is raised at r3d_create so that a
+// destroy -> create cycle (one per run of the host program's loop) reuses the memory instead of going to the driver.
 template <class T>
 int dev_alloc(DevState &D, T **p, size_t count) {
   void *q = nullptr;
-  CK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  CK(cudaMallocAsync(&q, std::max<size_t>(count, 1) * sizeof(T), D.stream));
   D.allocs.push_back(q);
   *p = static_cast<T *>(q);
   return 0;
@@ -223,11 +226,16 @@ int dev_upload(DevState &D, const T **p, const T *host, size_t count) {
 }
 
 typedef void (*propagate_fn)(const DevModel, const Job, uint32_t, uint32_t, unsigned long long *, unsigned long long *);
-propagate_fn pick_propagate(uint32_t kind, bool trace) {
+template <class Cell>
+propagate_fn pick_propagate_of(bool trace, bool small) {
+  if (small) return trace ? propagate_kernel<Cell, true, true> : propagate_kernel<Cell, false, true>;
+  return trace ? propagate_kernel<Cell, true, false> : propagate_kernel<Cell, false, false>;
+}
+propagate_fn pick_propagate(uint32_t kind, bool trace, bool small) {
   switch (kind) {
-    case R3D_CELL_CYLINDER: return trace ? propagate_kernel<Cylinder, true> : propagate_kernel<Cylinder, false>;
-    case R3D_CELL_SHELL: return trace ? propagate_kernel<Shell, true> : propagate_kernel<Shell, false>;
-    default: return trace ? propagate_kernel<Tetra, true> : propagate_kernel<Tetra, false>;
+    case R3D_CELL_CYLINDER: return pick_propagate_of<Cylinder>(trace, small);
+    case R3D_CELL_SHELL: return pick_propagate_of<Shell>(trace, small);
+    default: return pick_propagate_of<Tetra>(trace, small);
   }
 }
 
@@ -332,6 +340,21 @@ int env_int(const char *name, int dflt) {
 int build_device(DevState &D, const r3d_model_desc *d) {
   CK(cudaSetDevice(D.device));
   CK(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
+  {
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, D.device));
+    unsigned long long keep = ~0ull;
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  const bool timing = env_int("R3D_TIMING", 0) != 0;
+  auto t_start = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    cudaStreamSynchronize(D.stream);
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "r3d_create: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_start).count());
+    t_start = now;
+  };
   D.cell_kind = d->cell_kind;
   DevModel &M = D.M;
   memset(&M, 0, sizeof M);
@@ -353,6 +376,7 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   pack_toa_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, D.stream>>>(th, ph, toa, (uint32_t)nt, d->min_theta, d->max_theta);
   M.toa = toa;
 
+  lap("stream, pool, toa");
   if (int rc = dev_upload(D, &M.src_cdf, d->src_cdf, 3 * nt)) return rc;
   if (int rc = dev_upload(D, &M.scat_mfp, d->scat_mfp, 2 * ns)) return rc;
   if (int rc = dev_upload(D, &M.scat_whole, d->scat_whole_cdf, 8 * ns)) return rc;
@@ -365,6 +389,7 @@ int build_device(DevState &D, const r3d_model_desc *d) {
     pack_spol_kernel<<<(unsigned)((ns * nt + 255) / 256), 256, 0, D.stream>>>(spol_raw, spol, ns * nt);
     M.scat_spol = spol;
   }
+  lap("cdf tables, spol");
   if (int rc = dev_upload(D, &M.cell_params, d->cell_params, nc * d->cell_nparam)) return rc;
   if (int rc = dev_upload(D, &M.cell_scat, d->cell_scat, nc)) return rc;
   if (int rc = dev_upload(D, &M.face_flags, d->face_flags, nc * nf)) return rc;
@@ -376,6 +401,7 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   M.seis_sphere = sph;
   if (int rc = build_seis_grid(D, d)) return rc;
 
+  lap("cells, seismometer grid");
   // guide tables: exact only for non-decreasing CDFs; otherwise fall back to the plain bisection
   int *bad = nullptr;
   if (int rc = dev_alloc(D, &bad, 1)) return rc;
@@ -409,6 +435,7 @@ int build_device(DevState &D, const r3d_model_desc *d) {
     M.src_guide = gs; M.scat_guide = gc;
   }
 
+  lap("monotone check, guide tables");
   // accumulators
   const size_t nb = std::max<size_t>((size_t)d->n_seis * d->n_bins, 1);
   if (int rc = dev_alloc(D, &M.energies, nb * R3D_BIN_NF64)) return rc;
@@ -419,19 +446,22 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   CK(cudaMemsetAsync(M.counts, 0, nb * R3D_BIN_NCNT * sizeof(unsigned long long), D.stream));
   CK(cudaMemsetAsync(M.counters, 0, R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
 
+  lap("accumulators");
   // launch geometry: persistent CTAs, `blocks_per_sm` per SM, each with an equal share of the SM's shared memory
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, D.device));
+  struct { int multiProcessorCount, sharedMemPerMultiprocessor, reservedSharedMemPerBlock, sharedMemPerBlockOptin; } prop;
+  CK(cudaDeviceGetAttribute(&prop.multiProcessorCount, cudaDevAttrMultiProcessorCount, D.device));   // (cudaGetDeviceProperties takes 20+ ms)
+  CK(cudaDeviceGetAttribute(&prop.sharedMemPerMultiprocessor, cudaDevAttrMaxSharedMemoryPerMultiprocessor, D.device));
+  CK(cudaDeviceGetAttribute(&prop.reservedSharedMemPerBlock, cudaDevAttrReservedSharedMemoryPerBlock, D.device));
+  CK(cudaDeviceGetAttribute(&prop.sharedMemPerBlockOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, D.device));
   D.threads = std::min(R3D_NT, std::max(32, env_int("R3D_THREADS", 512) / 32 * 32));
   D.blocks_per_sm = std::max(1, env_int("R3D_BLOCKS_PER_SM", 1));
   cudaFuncAttributes fattr;
-  CK(cudaFuncGetAttributes(&fattr, pick_propagate(d->cell_kind, true)));
+  CK(cudaFuncGetAttributes(&fattr, pick_propagate(d->cell_kind, true, true)));
   const size_t per_block = (size_t)prop.sharedMemPerMultiprocessor / D.blocks_per_sm - (size_t)prop.reservedSharedMemPerBlock - fattr.sharedSizeBytes;
   D.smem_block = std::min(per_block, (size_t)prop.sharedMemPerBlockOptin - fattr.sharedSizeBytes) / 16 * 16;
-  const size_t cell_bytes = nc * d->cell_nparam * sizeof(double);
-  D.cell_doubles = 0;                      // cell parameters are read through L1 (r3d_resident.cuh)
-  (void)cell_bytes;
-  const size_t for_slots = D.smem_block - (size_t)D.cell_doubles * 8;
+  const uint32_t tb = Tab<true>::bytes(d->n_cells, d->cell_nparam, d->faces_per_cell, d->n_scat);
+  D.table_bytes = ((size_t)nc * d->cell_nparam * 8 + (size_t)ns * 80 <= (size_t)env_int("R3D_SMALL_TABLE_BYTES", 24 * 1024)) ? tb : 0u;
+  const size_t for_slots = D.smem_block - D.table_bytes;
   D.max_slots[0] = (uint32_t)std::min<size_t>(for_slots / R3D_SLOT_BYTES / 32 * 32, 65504);
   D.max_slots[1] = (uint32_t)std::min<size_t>(for_slots / R3D_SLOT_BYTES_TRACE / 32 * 32, 65504);
   if (int cap = env_int("R3D_SLOTS_PER_BLOCK", 0)) {
@@ -439,15 +469,16 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   }
   if (D.max_slots[1] < 32) return fail(R3D_EUNSUPPORTED, "shared memory too small for the phonon slots");
   for (int trace = 0; trace < 2; trace++)
-    CK(cudaFuncSetAttribute(pick_propagate(d->cell_kind, trace != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_block));
+    CK(cudaFuncSetAttribute(pick_propagate(d->cell_kind, trace != 0, D.table_bytes != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_block));
   D.grid = prop.multiProcessorCount * D.blocks_per_sm;
   if (int rc = dev_alloc(D, &D.block_tally, (size_t)D.grid * R3D_NCOUNTERS)) return rc;
-  if (int rc = dev_alloc(D, &D.block_clock, (size_t)D.grid * 3)) return rc;
+  if (int rc = dev_alloc(D, &D.block_clock, (size_t)D.grid * R3D_NCLOCKS)) return rc;
   CK(cudaMemsetAsync(D.block_tally, 0, (size_t)D.grid * R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
-  CK(cudaMemsetAsync(D.block_clock, 0, (size_t)D.grid * 3 * sizeof(unsigned long long), D.stream));
+  CK(cudaMemsetAsync(D.block_clock, 0, (size_t)D.grid * R3D_NCLOCKS * sizeof(unsigned long long), D.stream));
 
   CK(cudaStreamSynchronize(D.stream));
   CK(cudaGetLastError());
+  lap("launch geometry");
   return 0;
 }
 
@@ -467,12 +498,12 @@ int run_job(DevState &D, const JobReq &jr) {
     uint32_t S = D.max_slots[trace ? 1 : 0];
     const unsigned long long share = (jr.n + (unsigned long long)D.grid - 1) / (unsigned long long)D.grid;
     if (share < S) S = (uint32_t)((share + 31ull) / 32ull * 32ull);
-    const size_t smem = (size_t)S * (trace ? R3D_SLOT_BYTES_TRACE : R3D_SLOT_BYTES) + (size_t)D.cell_doubles * 8;
+    const size_t smem = (size_t)S * (trace ? R3D_SLOT_BYTES_TRACE : R3D_SLOT_BYTES) + D.table_bytes;
     const unsigned long long need = (jr.n + S - 1) / S;
     const int grid = (int)std::min<unsigned long long>((unsigned long long)D.grid, need);
     CK(cudaMemsetAsync(D.M.next_phonon, 0, sizeof(unsigned long long), D.stream));
     CK(cudaEventRecord(ek0, D.stream));
-    pick_propagate(D.cell_kind, trace)<<<grid, D.threads, smem, D.stream>>>(D.M, J, S, D.cell_doubles, D.block_tally, D.block_clock);
+    pick_propagate(D.cell_kind, trace, D.table_bytes != 0)<<<grid, D.threads, smem, D.stream>>>(D.M, J, S, D.table_bytes, D.block_tally, D.block_clock);
     CK(cudaEventRecord(ek1, D.stream));
     D.launches += 1;
   }
@@ -547,7 +578,8 @@ void destroy_device(DevState *D) {
   if (D->device >= 0) {
     cudaSetDevice(D->device);
     if (D->stream) cudaStreamSynchronize(D->stream);
-    for (void *p : D->allocs) cudaFree(p);
+    for (void *p : D->allocs) cudaFreeAsync(p, D->stream);
+    if (D->stream) cudaStreamSynchronize(D->stream);
     if (D->stream) cudaStreamDestroy(D->stream);
   }
   delete D;
@@ -701,7 +733,7 @@ int r3d_set_profiling(r3d_handle *h, int on) {
   for (DevState *D : h->devs) {
     if (int rc = drain(*D)) return rc;
     CK(cudaSetDevice(D->device));
-    CK(cudaMemsetAsync(D->block_clock, 0, (size_t)D->grid * 3 * sizeof(unsigned long long), D->stream));
+    CK(cudaMemsetAsync(D->block_clock, 0, (size_t)D->grid * R3D_NCLOCKS * sizeof(unsigned long long), D->stream));
     CK(cudaStreamSynchronize(D->stream));
     std::lock_guard<std::mutex> lk(D->mu);
     D->k_seconds = 0; D->k_launches = 0;
@@ -716,10 +748,22 @@ int r3d_kernel_times(r3d_handle *h, double seconds[3], uint64_t launches[3], uin
   unsigned long long k[R3D_NCOUNTERS];
   CK(cudaSetDevice(D.device));
   CK(cudaMemcpy(k, D.M.counters, sizeof k, cudaMemcpyDeviceToHost));
-  std::vector<unsigned long long> clk((size_t)D.grid * 3);
+  std::vector<unsigned long long> clk((size_t)D.grid * R3D_NCLOCKS);
   CK(cudaMemcpy(clk.data(), D.block_clock, clk.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   unsigned long long c1 = 0, c2 = 0, it = 0;
-  for (int b = 0; b < D.grid; b++) { c1 += clk[3 * b]; c2 += clk[3 * b + 1]; it = std::max(it, clk[3 * b + 2]); }
+  for (int b = 0; b < D.grid; b++) { c1 += clk[R3D_NCLOCKS * b]; c2 += clk[R3D_NCLOCKS * b + 1]; it = std::max(it, clk[R3D_NCLOCKS * b + 2]); }
+  if (env_int("R3D_TIMING", 0)) {          // warp-cycles by kind of chunk, summed over CTAs
+    unsigned long long k[R3D_NCLOCKS] = {0};
+    for (int b = 0; b < D.grid; b++) for (int i = 0; i < R3D_NCLOCKS; i++) k[i] += clk[R3D_NCLOCKS * b + i];
+    const char *nm[4] = {"advance", "refill", "face", "draw"};
+    double tot = (double)k[11];
+    for (int i = 0; i < 4; i++) tot += (double)k[3 + i];
+    for (int i = 0; i < 4; i++)
+      fprintf(stderr, "r3d chunks: %-8s %10llu chunks, %8.0f cycles each, %5.1f %% of warp time\n", nm[i], k[7 + i],
+              k[7 + i] ? (double)k[3 + i] / (double)k[7 + i] : 0.0, 100.0 * (double)k[3 + i] / tot);
+    fprintf(stderr, "r3d chunks: waiting at barriers / for work: %5.1f %% of warp time; phase 1 %.0f, phase 2 %.0f cycles per iteration\n",
+            100.0 * (double)k[11] / tot, (double)c1 / (double)std::max(1ull, k[2]), (double)c2 / (double)std::max(1ull, k[2]));
+  }
   std::lock_guard<std::mutex> lk(D.mu);
   const double tot = (double)(c1 + c2);
   seconds[0] = D.k_seconds;                                   // the propagate kernel, CUDA events on its stream

@@ -86,7 +86,7 @@ struct Tally {
 extern __shared__ __align__(16) unsigned char r3d_smem[];
 template <bool TRACE>
 struct Slots {
-  uint32_t S, cell_doubles;
+  uint32_t S, table_bytes;      // table_bytes: the staged small-model tables (multiple of 16; 0 = none)
   R3D_DEV double2 &tp(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem)[s]; }                     // (time alive, path length)
   R3D_DEV double2 &ra(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 16)[s]; }    // (recent travel time, attenuation exponent)
   R3D_DEV double2 &lxy(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 32)[s]; }   // location x, y
@@ -99,19 +99,25 @@ struct Slots {
   // the queued request: draw {31-bit draw, table | kind}; face {draw for the S-polarisation choice, draw for the
   // outcome choice}, exit face id in the two top bits
   R3D_DEV uint2 &req(uint32_t s) const { return reinterpret_cast<uint2 *>(r3d_smem + (size_t)S * 128)[s]; }
-  R3D_DEV double *cells() const { return reinterpret_cast<double *>(r3d_smem + (size_t)S * 136); }               // staged cell parameters
+  R3D_DEV unsigned char *tables() const { return r3d_smem + (size_t)S * 136; }                                   // staged small-model tables (Tab)
   // trace mode only: [3][S] catches, scatters, iterations
-  R3D_DEV uint32_t &tr(int which, uint32_t s) const { return reinterpret_cast<uint32_t *>(r3d_smem + (size_t)S * 136 + (size_t)cell_doubles * 8)[(uint32_t)which * S + s]; }
+  R3D_DEV uint32_t &tr(int which, uint32_t s) const { return reinterpret_cast<uint32_t *>(r3d_smem + (size_t)S * 136 + table_bytes)[(uint32_t)which * S + s]; }
   // queues of slot indices: buffer 0 / 1 = [cur|next] ready-to-advance slots from the front, free slots from the back;
   // buffer 2 = table draws: scatter draws from the front, source draws from the back; buffer 3 = face events: P from
   // the front, S from the back
   R3D_DEV uint16_t *queue(uint32_t buf) const {
-    return reinterpret_cast<uint16_t *>(r3d_smem + (size_t)S * (TRACE ? 148 : 136) + (size_t)cell_doubles * 8) + (size_t)buf * S;
+    return reinterpret_cast<uint16_t *>(r3d_smem + (size_t)S * (TRACE ? 148 : 136) + table_bytes) + (size_t)buf * S;
   }
 };
 
 // counters of the queues: cnt[0..3] = {advance, free} x {buffer 0, buffer 1}; cnt[4..7] = scatter draws, source draws, P faces, S faces
+// per-CTA clocks written at the end of a launch: [0] cycles in phase 1, [1] cycles in phase 2, [2] iterations,
+// [3..6] warp-cycles inside advance / refill / face / draw chunks, [7..10] number of such chunks, [11] warp-cycles
+// spent outside chunks (barriers, waiting for the last chunk of a phase)
+#define R3D_NCLOCKS 12
 struct Ctl {
+  unsigned long long t_kind[4], t_idle;
+  uint32_t n_kind[4];
   unsigned long long base;          // first phonon (relative to the job) granted to this CTA in this iteration
   uint32_t granted, exhausted, done, cursor[2];
   uint32_t cnt[8];
@@ -119,6 +125,74 @@ struct Ctl {
   uint32_t iterations;
 };
 enum { CNT_SCAT = 4, CNT_SRC, CNT_FP, CNT_FS };
+
+// ---- the small per-model tables every event reads: cell parameters, cell -> scatterer, face flags and neighbours,
+// mean free paths, conversion probabilities.  Layered and shell models have tens of cells (a few KB): SMALL stages
+// them in shared memory, because the table gathers of phase 2 stream through the (small) L1 and would otherwise
+// turn each of these reads into an L2 round trip in the middle of an event.  The tetrahedral models (2275 cells,
+// 0.7 MB) read them through L1 / L2.
+template <bool SMALL>
+struct Tab {
+  uint32_t base, np, nf, o_mfp, o_whole, o_other, o_scat, o_flags;     // byte offsets into r3d_smem
+  R3D_DEV void init(const DevModel &M, uint32_t base_) {
+    base = base_; np = M.cell_nparam; nf = M.faces_per_cell;
+    o_mfp = base + M.n_cells * np * 8u;
+    o_whole = o_mfp + M.n_scat * 16u;
+    o_other = o_whole + M.n_scat * 64u;
+    o_scat = o_other + M.n_cells * nf * 4u;
+    o_flags = o_scat + M.n_cells * 4u;
+  }
+  static __host__ __device__ uint32_t bytes(uint32_t n_cells, uint32_t np, uint32_t nf, uint32_t n_scat) {
+    return (n_cells * np * 8u + n_scat * 80u + n_cells * nf * 5u + n_cells * 4u + 15u) / 16u * 16u;
+  }
+  R3D_DEV void stage(const DevModel &M) const {          // all threads of the CTA; followed by a barrier
+    if (!SMALL) return;
+    double *d = reinterpret_cast<double *>(r3d_smem + base);
+    for (uint32_t i = threadIdx.x; i < M.n_cells * np; i += blockDim.x) d[i] = M.cell_params[i];
+    d = reinterpret_cast<double *>(r3d_smem + o_mfp);
+    for (uint32_t i = threadIdx.x; i < M.n_scat * 2u; i += blockDim.x) d[i] = M.scat_mfp[i];
+    d = reinterpret_cast<double *>(r3d_smem + o_whole);
+    for (uint32_t i = threadIdx.x; i < M.n_scat * 8u; i += blockDim.x) d[i] = M.scat_whole[i];
+    uint32_t *u = reinterpret_cast<uint32_t *>(r3d_smem + o_other);
+    for (uint32_t i = threadIdx.x; i < M.n_cells * nf; i += blockDim.x) u[i] = M.face_other[i];
+    u = reinterpret_cast<uint32_t *>(r3d_smem + o_scat);
+    for (uint32_t i = threadIdx.x; i < M.n_cells; i += blockDim.x) u[i] = M.cell_scat[i];
+    uint8_t *b = r3d_smem + o_flags;
+    for (uint32_t i = threadIdx.x; i < M.n_cells * nf; i += blockDim.x) b[i] = M.face_flags[i];
+  }
+  R3D_DEV const double *cell(const DevModel &M, uint32_t i) const {
+    if (SMALL) return reinterpret_cast<const double *>(r3d_smem + base) + i * np;
+    return M.cell_params + (size_t)i * np;
+  }
+  R3D_DEV double mfp(const DevModel &M, uint32_t scat, int type) const {
+    if (SMALL) return reinterpret_cast<const double *>(r3d_smem + o_mfp)[scat * 2u + (uint32_t)type];
+    return __ldg(M.scat_mfp + scat * 2u + (uint32_t)type);
+  }
+  R3D_DEV const double *whole(const DevModel &M, uint32_t scat, int type) const {
+    if (SMALL) return reinterpret_cast<const double *>(r3d_smem + o_whole) + (scat * 2u + (uint32_t)type) * 4u;
+    return M.scat_whole + (scat * 2u + (uint32_t)type) * 4u;
+  }
+  R3D_DEV uint32_t other(const DevModel &M, uint32_t fi) const {
+    if (SMALL) return reinterpret_cast<const uint32_t *>(r3d_smem + o_other)[fi];
+    return __ldg(M.face_other + fi);
+  }
+  R3D_DEV uint32_t scat(const DevModel &M, uint32_t cell) const {
+    if (SMALL) return reinterpret_cast<const uint32_t *>(r3d_smem + o_scat)[cell];
+    return __ldg(M.cell_scat + cell);
+  }
+  R3D_DEV uint32_t flags(const DevModel &M, uint32_t fi) const {
+    if (SMALL) return (r3d_smem + o_flags)[fi];
+    return __ldg(M.face_flags + fi);
+  }
+};
+
+// The first of a draw's three dependent gathers is its guide entry.  Its address is known when the draw is queued (phase
+// 1), a whole phase before it is used: pull the sector into L2 then.
+R3D_DEV void prefetch_guide(const DevModel &M, bool is_src, uint32_t table, uint32_t kdraw) {
+  if (M.guide_shift >= 32) return;
+  const uint32_t *g = (is_src ? M.src_guide : M.scat_guide) + (size_t)table * M.guide_stride + (kdraw >> M.guide_shift);
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
+}
 
 // A warp takes the next 32-entry chunk of the current phase's work list
 R3D_DEV uint32_t next_chunk(uint32_t *cursor) {
@@ -141,15 +215,15 @@ R3D_DEV void write_final(const Slots<TRACE> &A, const Job &J, uint32_t s, const 
 
 // one 32-byte take-off-angle record through the read-only path (two 16-byte loads of the same sector)
 R3D_DEV double4 load_toa(const double4 *p) {
-  const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+  const double2 a = ld_table(reinterpret_cast<const double2 *>(p)), b = ld_table(reinterpret_cast<const double2 *>(p) + 1);
   return make_double4(a.x, a.y, b.x, b.y);
 }
 
 // CellFace::VelocityJump (media_cellface.cpp:83-99).  Equal velocities give exactly 0 in the reference too
 // (2*(0)/(v+v)); testing for that first keeps 0/x off the slow path of the FP64 division.
-template <class Cell>
-R3D_DEV double velocity_jump(const DevModel &M, const double *cells, uint32_t cell, uint32_t other, v3 loc) {
-  const double *c = cells + (size_t)cell * M.cell_nparam, *o = cells + (size_t)other * M.cell_nparam;
+template <class Cell, class TabT>
+R3D_DEV double velocity_jump(const DevModel &M, const TabT &tab, uint32_t cell, uint32_t other, v3 loc) {
+  const double *c = tab.cell(M, cell), *o = tab.cell(M, other);
   double v1 = Cell::veloc(c, 0, loc), v2 = Cell::veloc(o, 0, loc);
   double dvp = (v1 == v2 && v1 > 0.0) ? 0.0 : fabs(2 * (v2 - v1) / (v2 + v1));
   v1 = Cell::veloc(c, 1, loc); v2 = Cell::veloc(o, 1, loc);
@@ -160,28 +234,28 @@ R3D_DEV double velocity_jump(const DevModel &M, const double *cells, uint32_t ce
 // What happens at a face (phonons.cpp:629-676), decided where the phonon arrives so that the draws the face
 // event will consume can be taken from the stream in order.
 enum { FACE_NONE = 0, FACE_LOST, FACE_CONTINUOUS, FACE_BEND, FACE_FULLRT };
-template <class Cell>
-R3D_DEV int face_action(const DevModel &M, const double *cells, uint32_t fl, uint32_t cell, uint32_t other, v3 loc) {
+template <class Cell, class TabT>
+R3D_DEV int face_action(const DevModel &M, const TabT &tab, uint32_t fl, uint32_t cell, uint32_t other, v3 loc) {
   if (fl & R3D_FACE_REFLECT) return FACE_FULLRT;                                    // phonons.cpp:640-646
   if (fl & R3D_FACE_ADJOIN) {                                                       // Phonon::Refract, phonons.cpp:225-255
     if (fl & R3D_FACE_DISCON) return FACE_FULLRT;
-    return (velocity_jump<Cell>(M, cells, cell, other, loc) > 0.00001) ? FACE_BEND : FACE_CONTINUOUS;
+    return (velocity_jump<Cell>(M, tab, cell, other, loc) > 0.00001) ? FACE_BEND : FACE_CONTINUOUS;
   }
   return FACE_LOST;                                                                 // phonons.cpp:675
 }
 
 // Phonon::Refraction_FullRT (phonons.cpp:429-476) + CellFace::GetRTBasis (media_cellface.cpp:122-149)
-template <class Cell>
-R3D_DEV void refraction_fullrt(const DevModel &M, const double *cells, Phonon &p, int face, bool adjoin, uint32_t other,
+template <class Cell, class TabT>
+R3D_DEV void refraction_fullrt(const DevModel &M, const TabT &tab, Phonon &p, int face, bool adjoin, uint32_t other,
                                uint32_t k_spol, uint32_t k_choose) {
-  const double *c = cells + (size_t)p.cell * M.cell_nparam;
+  const double *c = tab.cell(M, p.cell);
   RTCoef rt;
   rt.init(Cell::normal(c, face, p.loc), p.dir);
   rt.densR = Cell::dens(c, p.loc);
   rt.velR[0] = Cell::veloc(c, 0, p.loc);
   rt.velR[1] = Cell::veloc(c, 1, p.loc);
   if (adjoin) {
-    const double *o = cells + (size_t)other * M.cell_nparam;
+    const double *o = tab.cell(M, other);
     rt.densT = Cell::dens(o, p.loc);
     rt.velT[0] = Cell::veloc(o, 0, p.loc);
     rt.velT[1] = Cell::veloc(o, 1, p.loc);
@@ -202,10 +276,10 @@ R3D_DEV void refraction_fullrt(const DevModel &M, const double *cells, Phonon &p
 }
 
 // Phonon::Refraction_Bend (phonons.cpp:311-405)
-template <class Cell>
-R3D_DEV void refraction_bend(const DevModel &M, const double *cells, Phonon &p, int face, uint32_t other) {
-  const double *c = cells + (size_t)p.cell * M.cell_nparam;
-  const double *o = cells + (size_t)other * M.cell_nparam;
+template <class Cell, class TabT>
+R3D_DEV void refraction_bend(const DevModel &M, const TabT &tab, Phonon &p, int face, uint32_t other) {
+  const double *c = tab.cell(M, p.cell);
+  const double *o = tab.cell(M, other);
   const v3 mdir = p.dir;
   const v3 fnorm = Cell::normal(c, face, p.loc);
   const v3 fpara = inplane_unit_perp(fnorm, mdir);
@@ -252,8 +326,8 @@ R3D_DEV void route(const Slots<TRACE> &A, Ctl &C, int nxt, int out, uint32_t s) 
 // =====================================================================================================
 // phase 1a: one Propagate-loop iteration up to the event's classification (phonons.cpp:542-623)
 // =====================================================================================================
-template <class Cell, bool TRACE>
-R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, const double *cells, uint32_t s, Tally &T) {
+template <class Cell, bool TRACE, class TabT>
+R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, const TabT &tab, uint32_t s, Tally &T) {
   Phonon p;
   const double2 tp = A.tp(s), ra = A.ra(s), lxy = A.lxy(s), lzdz = A.lzdz(s), dxy = A.dxy(s);
   const uint4 meta = A.meta(s);
@@ -281,7 +355,7 @@ R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
   }
   bool dir_changed = false, s1_loaded = false;
   if (!fate) {
-    const double *c = cells + (size_t)p.cell * M.cell_nparam;
+    const double *c = tab.cell(M, p.cell);
     typename Cell::Path P;
     const double edgelen = Cell::path(M, c, p.type, p.loc, p.dir, P);
     if (edgelen == pinf()) fate = R3D_FATE_TIMEOUT;             // phonons.cpp:595-598
@@ -293,10 +367,10 @@ R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
       g.block(b);
       const uint32_t w1 = g.w[1], w2 = g.w[2], w3 = g.w[3];
       const uint32_t k_path = ((o == 0) ? g.w[0] : (o == 1) ? w1 : (o == 2) ? w2 : w3) >> 1;
-      const uint32_t scat = __ldg(M.cell_scat + p.cell);
+      const uint32_t scat = tab.scat(M, p.cell);
       // Scatterer::GetRandomPathLength (scatterers.cpp:297-307)
-      const double r = 1.0 - ((double)k_path) / (kRandMax + 1);
-      const double scatlen = -log(r) * __ldg(M.scat_mfp + scat * 2 + p.type);
+      const double r = 1.0 - ((double)k_path) * (1.0 / 2147483648.0);      // k / (RAND_MAX + 1): a power of two, exact either way
+      const double scatlen = -log(r) * tab.mfp(M, scat, p.type);
       const bool scatter = scatlen < edgelen;
       const Travel tr = Cell::advance(M, c, p.type, scatter ? scatlen : edgelen, p.loc, p.dir, P);
       // Phonon::Move (phonons.cpp:62-70)
@@ -315,9 +389,9 @@ R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
         if (!M.no_deflect) more = 2;                              // conversion type, take-off angle (scatterers.cpp:332,336)
       } else {
         const uint32_t fi = p.cell * M.faces_per_cell + P.face;
-        fl = __ldg(M.face_flags + fi);
-        other = __ldg(M.face_other + fi);
-        action = face_action<Cell>(M, cells, fl, p.cell, other, p.loc);
+        fl = tab.flags(M, fi);
+        other = tab.other(M, fi);
+        action = face_action<Cell>(M, tab, fl, p.cell, other, p.loc);
         if (action == FACE_FULLRT) more = (p.type == R3D_RAY_S) ? 2 : 1;   // [S polarisation choice,] outcome choice
       }
       uint32_t k1 = 0, k2 = 0;
@@ -340,8 +414,9 @@ R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
           T.v[R3D_CNT_SCATTERS]++;
           if (TRACE) A.tr(1, s)++;
         } else {
-          const uint32_t conv = cdf_search_small(M.scat_whole + (scat * 2 + p.type) * 4, 4, k1);
+          const uint32_t conv = cdf_search_small(tab.whole(M, scat, p.type), 4, k1);
           A.req(s) = make_uint2(k2, scat * 4 + conv);
+          prefetch_guide(M, false, scat * 4 + conv, k2);
           out = OUT_SCAT;
         }
       } else if (action == FACE_LOST && !(fl & R3D_FACE_COLLECT)) fate = R3D_FATE_LOST;
@@ -384,6 +459,7 @@ R3D_DEV void refill_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
   g.block(0);
   const uint32_t rt3 = cdf_search_small(M.src_whole, 3, g.w[0] >> 1);
   A.req(s) = make_uint2(g.w[1] >> 1, rt3);                    // the take-off angle is drawn in phase 2
+  prefetch_guide(M, true, rt3, g.w[1] >> 1);
   A.tp(s) = make_double2(0.0, 0.0);
   A.ra(s) = make_double2(0.0, 0.0);
   A.lxy(s) = make_double2(M.src_loc[0], M.src_loc[1]);
@@ -396,35 +472,124 @@ R3D_DEV void refill_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
 
 // =====================================================================================================
 // phase 2a: ProbDist::GetRandomIndex on the queued table + take-off angle, then either the new phonon's
-// direction (sources.cpp:156-170) or Phonon::Transform (phonons.cpp:116-170)
+// direction (sources.cpp:156-170) or Phonon::Transform (phonons.cpp:116-170).
+// A draw is a chain of three dependent gathers from HBM / L2 (guide entry -> CDF entries -> take-off angle).  A thread
+// works on U draws at once and issues each stage's loads for all of them before it consumes any, so a warp has
+// 32 U chains in flight instead of 32 (ncu: with one draw per thread phase 2 took two thirds of the kernel, waiting).
 // =====================================================================================================
-template <bool TRACE>
-R3D_DEV void draw_one(const DevModel &M, const Slots<TRACE> &A, uint32_t s, bool is_src, Tally &T) {
-  const uint2 q = A.req(s);
-  if (is_src) {
-    // new phonon: direction = the drawn take-off angle, polarisation angle pi/2 for SH else 0 (phonons.hpp:193-207)
-    const uint32_t ti = cdf_search(M.src_cdf + (size_t)q.y * M.n_toa, M.n_toa, M.src_guide + (size_t)q.y * M.guide_stride, M.guide_shift, q.x);
-    const double4 t = load_toa(M.toa + ti);                   // sin th, cos th, sin ph, cos ph
-    A.dxy(s) = make_double2(t.x * t.w, t.x * t.z);
-    A.lzdz(s).y = t.y;
-    if (q.y == R3D_RAY_SH) { A.sxy(s) = make_double2(-t.z, t.w); A.sz(s) = 0.0; }                 // phi-hat
-    else { A.sxy(s) = make_double2(t.y * t.w, t.y * t.z); A.sz(s) = -t.x; }                       // theta-hat
+#ifndef R3D_DRAW_U
+#define R3D_DRAW_U 1
+#endif
+template <bool TRACE, int U>
+R3D_DEV void draw_batch(const DevModel &M, const Slots<TRACE> &A, const uint16_t *q, bool from_back, uint32_t j0, uint32_t count,
+                        bool is_src, Tally &T, uint32_t (&s)[U], bool (&have)[U]) {
+  const unsigned lane = threadIdx.x & 31u;
+  const double *cdf0 = is_src ? M.src_cdf : M.scat_cdf;
+  const uint32_t *guide0 = is_src ? M.src_guide : M.scat_guide;
+  uint32_t kd[U], tbl[U], ti[U];
+  const double *cdf[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const uint32_t j = j0 + (uint32_t)u * 32u + lane;
+    have[u] = j < count;
+    s[u] = have[u] ? (uint32_t)q[from_back ? A.S - 1u - j : j] : 0u;
+    const uint2 rq = have[u] ? A.req(s[u]) : make_uint2(0u, 0u);
+    kd[u] = rq.x; tbl[u] = rq.y;
+    cdf[u] = cdf0 + (size_t)tbl[u] * M.n_toa;
+  }
+  if (M.guide_shift < 32) {
+    // cdf_search_guided (r3d_device.cuh), stage by stage over the U draws
+    uint32_t k1[U], k2[U];
+    double r[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint32_t *g = guide0 + (size_t)tbl[u] * M.guide_stride + (kd[u] >> M.guide_shift);
+      k1[u] = ld_table(g); k2[u] = ld_table(g + 1);
+      r[u] = ld_table(cdf[u] + (M.n_toa - 1));
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) r[u] = r[u] * over_randmax(kd[u]);
+    // Wide buckets (they cover low-probability entries): narrow 8-fold per round trip with seven independent probes
+    // (same predicate, cdf non-decreasing), for all U draws in lockstep so that the probes of one round overlap.
+    for (;;) {
+      bool wide = false;
+#pragma unroll
+      for (int u = 0; u < U; u++) wide |= (k2[u] - k1[u] > 4);
+      if (!__any_sync(R3D_FULL, wide)) break;
+      double pv[U][7];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t span = k2[u] - k1[u];
+#pragma unroll
+        for (uint32_t i = 0; i < 7; i++)
+          pv[u][i] = (span > 4) ? ld_table(cdf[u] + k1[u] + (uint32_t)(((unsigned long long)span * (i + 1)) >> 3)) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t span = k2[u] - k1[u];
+        if (span > 4) {
+          uint32_t c = 0;
+#pragma unroll
+          for (uint32_t i = 0; i < 7; i++) c += (r[u] <= pv[u][i]) ? 0u : 1u;
+          // probes 0..c-1 are below r, probe c (if any) is the first one at or above it
+          uint32_t lo = k1[u], hi = k2[u];
+#pragma unroll
+          for (uint32_t i = 0; i < 7; i++) {
+            const uint32_t pr = k1[u] + (uint32_t)(((unsigned long long)span * (i + 1)) >> 3);
+            if (i + 1 == c) lo = pr + 1;
+            if (i == c) hi = pr;
+          }
+          k1[u] = lo; k2[u] = hi;
+        }
+      }
+    }
+    double v[U][4];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (uint32_t i = 0; i < 4; i++) v[u][i] = (k1[u] + i < k2[u]) ? ld_table(cdf[u] + k1[u] + i) : pinf();
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      uint32_t c = 0;
+#pragma unroll
+      for (uint32_t i = 0; i < 4; i++) c += (r[u] <= v[u][i]) ? 0u : 1u;
+      ti[u] = k1[u] + c;
+    }
   } else {
-    const uint32_t ti = cdf_search(M.scat_cdf + (size_t)q.y * M.n_toa, M.n_toa, M.scat_guide + (size_t)q.y * M.guide_stride, M.guide_shift, q.x);
-    const double4 t = load_toa(M.toa + ti);
-    const uint32_t conv = q.y & 3u;
-    double2 rp = make_double2(1.0, 0.0);                        // (cos, sin) of the relative polarisation angle
-    if (conv == 3u) rp = __ldg(M.scat_spol + (size_t)(q.y >> 2) * M.n_toa + ti);
-    const double2 dxy = A.dxy(s), sxy = A.sxy(s);
-    v3 e3 = V(dxy.x, dxy.y, A.lzdz(s).y), s1 = V(sxy.x, sxy.y, A.sz(s));
-    transform(e3, s1, t.x, t.y, t.z, t.w, rp.y, rp.x);
-    A.dxy(s) = make_double2(e3.x, e3.y);
-    A.lzdz(s).y = e3.z;
-    A.sxy(s) = make_double2(s1.x, s1.y);
-    A.sz(s) = s1.z;
-    A.meta(s).w = conv & 1u;                                  // PP,PS,SP,SS -> P,S,P,S
-    T.v[R3D_CNT_SCATTERS]++;
-    if (TRACE) A.tr(1, s)++;
+#pragma unroll
+    for (int u = 0; u < U; u++) ti[u] = cdf_search_plain(cdf[u], M.n_toa, kd[u]);
+  }
+  double4 t[U];
+  double2 rp[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    t[u] = load_toa(M.toa + ti[u]);                           // sin th, cos th, sin ph, cos ph
+    rp[u] = make_double2(1.0, 0.0);                           // (cos, sin) of the relative polarisation angle
+    if (!is_src && (tbl[u] & 3u) == 3u) rp[u] = ld_table(M.scat_spol + (size_t)(tbl[u] >> 2) * M.n_toa + ti[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    if (!have[u]) continue;
+    const uint32_t su = s[u];
+    if (is_src) {
+      // new phonon: direction = the drawn take-off angle, polarisation angle pi/2 for SH else 0 (phonons.hpp:193-207)
+      A.dxy(su) = make_double2(t[u].x * t[u].w, t[u].x * t[u].z);
+      A.lzdz(su).y = t[u].y;
+      if (tbl[u] == R3D_RAY_SH) { A.sxy(su) = make_double2(-t[u].z, t[u].w); A.sz(su) = 0.0; }                     // phi-hat
+      else { A.sxy(su) = make_double2(t[u].y * t[u].w, t[u].y * t[u].z); A.sz(su) = -t[u].x; }                     // theta-hat
+    } else {
+      const uint32_t conv = tbl[u] & 3u;
+      const double2 dxy = A.dxy(su), sxy = A.sxy(su);
+      v3 e3 = V(dxy.x, dxy.y, A.lzdz(su).y), s1 = V(sxy.x, sxy.y, A.sz(su));
+      transform(e3, s1, t[u].x, t[u].y, t[u].z, t[u].w, rp[u].y, rp[u].x);
+      A.dxy(su) = make_double2(e3.x, e3.y);
+      A.lzdz(su).y = e3.z;
+      A.sxy(su) = make_double2(s1.x, s1.y);
+      A.sz(su) = s1.z;
+      A.meta(su).w = conv & 1u;                               // PP,PS,SP,SS -> P,S,P,S
+      T.v[R3D_CNT_SCATTERS]++;
+      if (TRACE) A.tr(1, su)++;
+    }
   }
 }
 
@@ -432,8 +597,8 @@ R3D_DEV void draw_one(const DevModel &M, const Slots<TRACE> &A, uint32_t s, bool
 // phase 2b: everything that happens at a face that is not a plain hand-over: collection (dataout.cpp:545-568,
 // 103-216), free-surface / discontinuity R/T (phonons.cpp:429-476), Snell bending (phonons.cpp:311-405)
 // =====================================================================================================
-template <class Cell, bool TRACE>
-R3D_DEV int face_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, const double *cells, uint32_t s, Tally &T) {
+template <class Cell, bool TRACE, class TabT>
+R3D_DEV int face_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, const TabT &tab, uint32_t s, Tally &T) {
   Phonon p;
   const double2 tp = A.tp(s), ra = A.ra(s), lxy = A.lxy(s), lzdz = A.lzdz(s), dxy = A.dxy(s), sxy = A.sxy(s);
   const uint4 meta = A.meta(s);
@@ -446,7 +611,7 @@ R3D_DEV int face_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, con
   const int face = (int)((q.x >> 31) | ((q.y >> 31) << 1));
   const uint32_t k_spol = q.x & 0x7fffffffu, k_choose = q.y & 0x7fffffffu;
   const uint32_t fi = p.cell * M.faces_per_cell + face;
-  const uint32_t fl = __ldg(M.face_flags + fi), other = __ldg(M.face_other + fi);
+  const uint32_t fl = tab.flags(M, fi), other = tab.other(M, fi);
 
   // ---- collection (dataout.cpp:545-568): every seismometer is pass-through (dataout.cpp:50), so all that contain
   // the point must bin it.  Candidates come from the uniform grid over the seismometers' bounding spheres. --------
@@ -465,7 +630,7 @@ R3D_DEV int face_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, con
         const double ddx = qa.x - p.loc.x, ddy = qa.y - p.loc.y, ddz = qb.x - p.loc.z;
         if (ddx * ddx + ddy * ddy + ddz * ddz > qb.y) continue;   // cannot be within the gather radius
         // rare from here on (a few per cent of the surface hits): the exact CatchPhonon test
-        const double vel = Cell::veloc(cells + (size_t)p.cell * M.cell_nparam, p.type, p.loc);
+        const double vel = Cell::veloc(tab.cell(M, p.cell), p.type, p.loc);
         const v3 dopm = (p.type == R3D_RAY_P) ? p.dir : p.s1;   // Phonon::DirectionOfMotion (phonons.cpp:201-211)
         uint32_t bin; double e[4];
         if (seis_catch(M.seis + (size_t)k2 * R3D_SEIS_NPARAM, M.bin_dt, M.n_bins, p.time, p.loc, p.dir, dopm, p.type, exp(-p.aexp), vel, bin, e)) {
@@ -484,9 +649,9 @@ R3D_DEV int face_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, con
   }
 
   // ---- reflection / refraction (phonons.cpp:640-676) ---------------------------------------------------
-  const int action = face_action<Cell>(M, cells, fl, p.cell, other, p.loc);
-  if (action == FACE_FULLRT) refraction_fullrt<Cell>(M, cells, p, face, (fl & R3D_FACE_ADJOIN) != 0, other, k_spol, k_choose);
-  else if (action == FACE_BEND) refraction_bend<Cell>(M, cells, p, face, other);
+  const int action = face_action<Cell>(M, tab, fl, p.cell, other, p.loc);
+  if (action == FACE_FULLRT) refraction_fullrt<Cell>(M, tab, p, face, (fl & R3D_FACE_ADJOIN) != 0, other, k_spol, k_choose);
+  else if (action == FACE_BEND) refraction_bend<Cell>(M, tab, p, face, other);
   else if (action == FACE_CONTINUOUS) p.cell = other;
   else {
     T.died(R3D_FATE_LOST);
@@ -504,25 +669,29 @@ R3D_DEV int face_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, con
 // =====================================================================================================
 // the kernel: persistent CTAs, S slots each
 // =====================================================================================================
-template <class Cell, bool TRACE>
+template <class Cell, bool TRACE, bool SMALL>
 __global__ void __launch_bounds__(R3D_NT, R3D_MINBLOCKS)
-propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t cell_doubles, unsigned long long *block_tally,
+propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes, unsigned long long *block_tally,
                  unsigned long long *block_clock) {
   __shared__ unsigned long long tally_sm[R3D_NT / 32][R3D_NCOUNTERS];
   __shared__ Ctl C;
-  Slots<TRACE> A; A.S = S; A.cell_doubles = cell_doubles;
-  const double *__restrict__ cells = M.cell_params;      // a few hundred bytes (layered models) to 0.7 MB (tetrahedra): L1 / L2 resident
+  Slots<TRACE> A; A.S = S; A.table_bytes = table_bytes;
+  Tab<SMALL> tab; tab.init(M, S * 136u);
+  tab.stage(M);
   for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) A.queue(0)[S - 1u - i] = (uint16_t)i;     // every slot starts free
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int k = 0; k < 8; k++) C.cnt[k] = 0;
     C.cnt[OUT_FREE] = S;
     C.exhausted = 0; C.done = 0; C.t_phase[0] = 0; C.t_phase[1] = 0; C.iterations = 0;
+    for (int k = 0; k < 4; k++) { C.t_kind[k] = 0; C.n_kind[k] = 0; }
+    C.t_idle = 0;
   }
   const unsigned lane = threadIdx.x & 31u;
   Tally T; T.clear();
   int cur = 0;
   long long t0 = 0;
+  const long long t_begin = clock64();
   __syncthreads();
 
   for (;;) {
@@ -557,14 +726,16 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t cell_double
         if (c >= cA + cR) break;
         int out = OUT_NONE;
         uint32_t s = 0;
+        const long long tc = clock64();
         if (c < cA) {
           const uint32_t j = c * 32u + lane;
-          if (j < nA) { s = q[j]; out = advance_one<Cell, TRACE>(M, J, A, cells, s, T); }
+          if (j < nA) { s = q[j]; out = advance_one<Cell, TRACE>(M, J, A, tab, s, T); }
         } else {
           const uint32_t j = (c - cA) * 32u + lane;
           if (j < nR) { s = q[S - 1u - j]; refill_one<TRACE>(M, J, A, s, base + j, T); out = OUT_SRC; }
         }
         route<TRACE>(A, C, nxt, out, s);
+        if (lane == 0) { const int kd = (c < cA) ? 0 : 1; atomicAdd(&C.t_kind[kd], (unsigned long long)(clock64() - tc)); atomicAdd(&C.n_kind[kd], 1u); }
       }
     }
     __syncthreads();
@@ -573,38 +744,46 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t cell_double
     // ---- phase 2: face chunks (S, then P), then draw chunks (scatter, then source) -----------------------------
     {
       const uint32_t nFS = C.cnt[CNT_FS], nFP = C.cnt[CNT_FP], nDS = C.cnt[CNT_SCAT], nDR = C.cnt[CNT_SRC];
-      const uint32_t c0 = (nFS + 31u) >> 5, c1 = c0 + ((nFP + 31u) >> 5), c2 = c1 + ((nDS + 31u) >> 5), c3 = c2 + ((nDR + 31u) >> 5);
+      constexpr uint32_t DB = 32u * R3D_DRAW_U;                 // draws per chunk
+      const uint32_t c0 = (nFS + 31u) >> 5, c1 = c0 + ((nFP + 31u) >> 5), c2 = c1 + (nDS + DB - 1u) / DB, c3 = c2 + (nDR + DB - 1u) / DB;
       const uint16_t *qd = A.queue(2), *qf = A.queue(3);
       for (;;) {
         const uint32_t c = next_chunk(&C.cursor[1]);
         if (c >= c3) break;
-        int out = OUT_NONE;
-        uint32_t s = 0;
-        if (c < c0) {
-          const uint32_t j = c * 32u + lane;
-          if (j < nFS) { s = qf[S - 1u - j]; out = face_one<Cell, TRACE>(M, J, A, cells, s, T); }
-        } else if (c < c1) {
-          const uint32_t j = (c - c0) * 32u + lane;
-          if (j < nFP) { s = qf[j]; out = face_one<Cell, TRACE>(M, J, A, cells, s, T); }
-        } else if (c < c2) {
-          const uint32_t j = (c - c1) * 32u + lane;
-          if (j < nDS) { s = qd[j]; draw_one<TRACE>(M, A, s, false, T); out = OUT_ADV; }
+        const long long tc = clock64();
+        if (c < c1) {
+          const bool from_back = c < c0;
+          const uint32_t j = (from_back ? c : c - c0) * 32u + lane, count = from_back ? nFS : nFP;
+          int out = OUT_NONE;
+          uint32_t s = 0;
+          if (j < count) { s = qf[from_back ? S - 1u - j : j]; out = face_one<Cell, TRACE>(M, J, A, tab, s, T); }
+          route<TRACE>(A, C, nxt, out, s);
         } else {
-          const uint32_t j = (c - c2) * 32u + lane;
-          if (j < nDR) { s = qd[S - 1u - j]; draw_one<TRACE>(M, A, s, true, T); out = OUT_ADV; }
+          const bool is_src = c >= c2;
+          uint32_t s[R3D_DRAW_U];
+          bool have[R3D_DRAW_U];
+          draw_batch<TRACE, R3D_DRAW_U>(M, A, qd, is_src, (is_src ? c - c2 : c - c1) * DB, is_src ? nDR : nDS, is_src, T, s, have);
+#pragma unroll
+          for (int u = 0; u < R3D_DRAW_U; u++) route<TRACE>(A, C, nxt, have[u] ? OUT_ADV : OUT_NONE, s[u]);
         }
-        route<TRACE>(A, C, nxt, out, s);
+        if (lane == 0) { const int kd = (c < c1) ? 2 : 3; atomicAdd(&C.t_kind[kd], (unsigned long long)(clock64() - tc)); atomicAdd(&C.n_kind[kd], 1u); }
       }
     }
     __syncthreads();
     if (threadIdx.x == 0) { C.t_phase[1] += (unsigned long long)(clock64() - t0); C.iterations++; }
     cur = nxt;
   }
-  T.flush(block_tally + (size_t)blockIdx.x * R3D_NCOUNTERS, tally_sm);
+  if (threadIdx.x == 0) {                    // warp time not spent inside chunks: barriers, waiting for a phase's last chunk
+    const unsigned long long all = (unsigned long long)(clock64() - t_begin) * (blockDim.x >> 5);
+    const unsigned long long busy = C.t_kind[0] + C.t_kind[1] + C.t_kind[2] + C.t_kind[3];
+    C.t_idle = all > busy ? all - busy : 0;
+  }
+  T.flush(block_tally + (size_t)blockIdx.x * R3D_NCOUNTERS, tally_sm);      // (contains a barrier)
   if (threadIdx.x == 0) {
-    block_clock[3 * blockIdx.x + 0] += C.t_phase[0];
-    block_clock[3 * blockIdx.x + 1] += C.t_phase[1];
-    block_clock[3 * blockIdx.x + 2] += C.iterations;
+    unsigned long long *bc = block_clock + (size_t)R3D_NCLOCKS * blockIdx.x;
+    bc[0] += C.t_phase[0]; bc[1] += C.t_phase[1]; bc[2] += C.iterations;
+    for (int k = 0; k < 4; k++) { bc[3 + k] += C.t_kind[k]; bc[7 + k] += C.n_kind[k]; }
+    bc[11] += C.t_idle;
   }
 }
 

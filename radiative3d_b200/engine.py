@@ -159,16 +159,19 @@ class Engine:
         return n.value
 
     def set_profiling(self, on=True):
-        """Bracket every kernel of the step loop with CUDA events (resets the per-kernel totals)."""
+        """Reset the kernel-time totals (the propagate kernel is always event-timed; `on` is ignored)."""
         _ck(self._L, self._L.r3d_set_profiling(self._h, 1 if on else 0))
 
     def kernel_times(self):
-        """{'advance'|'draw'|'interface': (device seconds, launches, units processed)} since set_profiling()."""
+        """Device slot 0 since the last set_profiling(): propagate-kernel seconds (CUDA events) and launches, the
+        seconds split into the CTAs' two phases, iterations of the busiest CTA, CTAs per launch, and the units the
+        kernel processed (loop events, table draws, bin updates) as tallied by the handle's counters."""
         t = np.zeros(3)
         n = np.zeros(3, dtype=np.uint64)
         u = np.zeros(3, dtype=np.uint64)
         _ck(self._L, self._L.r3d_kernel_times(self._h, _pd(t), abi.as_ptr(n, C.c_uint64), abi.as_ptr(u, C.c_uint64)))
-        return {name: (float(t[i]), int(n[i]), int(u[i])) for i, name in enumerate(("advance", "draw", "interface"))}
+        return {"seconds": float(t[0]), "launches": int(n[0]), "phase1_seconds": float(t[1]), "phase2_seconds": float(t[2]),
+                "iterations": int(n[1]), "ctas": int(n[2]), "events": int(u[0]), "draws": int(u[1]), "catches": int(u[2])}
 
     def stream(self, slot=0):
         s = C.c_void_p()

@@ -1,0 +1,15 @@
+#!/usr/bin/env python
+"""Scratch: warp-time by kind of chunk (R3D_TIMING=1 makes r3d_kernel_times print it).  usage: chunk_clocks.py <config> <deg> <n>"""
+import os, sys
+os.environ["R3D_TIMING"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from radiative3d_b200 import abi, engine, reference_host
+cfg, deg, n = sys.argv[1], int(sys.argv[2]), int(float(sys.argv[3]))
+m = reference_host.build_model(cfg, deg)
+eng = engine.Engine(m)
+eng.run_simulation(n, seed=1); eng.sync(); eng.reset(); eng.set_profiling(True)
+eng.run_simulation(n, seed=2)
+t = eng.sync()
+kt = eng.kernel_times()
+print(f"{cfg} deg {deg} n={n}: {t * 1e3:.2f} ms, {n / t:.3e} phonons/s; {kt}")

@@ -13,9 +13,6 @@ for w in $what; do case $w in
   launches) timeout 600 python bench.py $small > $out/plain_small.json 2>&1 && \
             timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv \
               python bench.py $small > $out/ncu_launches.log 2>&1; tail -1 $out/ncu_launches.log | cut -c1-200;;
-  ncu)      timeout 300 python scripts/profile_target.py halfspace_nearsrc50 9 2e7 > $out/plain_target.log 2>&1; cat $out/plain_target.log
-            for k in advance draw interface; do
-              timeout 600 ncu --set full --clock-control none --import-source on -k regex:${k}_kernel -s 40 -c 1 -f -o $out/prof_$k \
-                python scripts/profile_target.py halfspace_nearsrc50 9 2e7 > $out/ncu_$k.log 2>&1; tail -1 $out/ncu_$k.log
-            done;;
+  ncu)      scripts/gpu_ncu.sh $tag 2e7;;
+  create)   timeout 300 python scripts/time_create.py > $out/time_create.log 2>&1; cat $out/time_create.log;;
 esac; done

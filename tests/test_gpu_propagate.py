@@ -136,3 +136,18 @@ def test_device_accumulators_wrap_as_torch():
         assert np.array_equal(dc.cpu().numpy().astype(np.uint64).reshape(c.shape), c)
         assert np.array_equal(de.cpu().numpy().reshape(e.shape), e)
         assert int(dk[abi.R3D_CNT_PHONONS]) == 20000
+
+
+def test_kernel_times_report():
+    """The roofline hook: one event-timed launch per job, phase shares that add up, units equal to the counters."""
+    m, _ = load_golden("halfspace")
+    with engine.Engine(m) as eng:
+        eng.set_profiling(True)
+        eng.run_simulation(50000, seed=2)
+        eng.sync()
+        kt = eng.kernel_times()
+        e, c, k = eng.fetch()
+    assert kt["launches"] == 1 and kt["seconds"] > 0 and kt["iterations"] >= 1 and kt["ctas"] >= 1
+    assert abs(kt["phase1_seconds"] + kt["phase2_seconds"] - kt["seconds"]) <= 1e-9 + 1e-6 * kt["seconds"]
+    assert kt["events"] == int(k[abi.R3D_CNT_EVENTS]) and kt["catches"] == int(c.sum())
+    assert kt["draws"] == int(k[abi.R3D_CNT_SCATTERS]) + 50000
