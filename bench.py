@@ -214,11 +214,13 @@ def main():
         first, n = distributed.shard_range(i * per * world, per * world, rank, world)
         eng.run_simulation(n, seed=SEED, first_phonon=first)
 
+    de, dc, dk = (torch.as_tensor(v, device=f"cuda:{local}") for v in eng.device_accumulators(0))
     for i in range(W):
         enqueue(i)
     eng.sync()
+    distributed.all_reduce_results(de, dc, dk)        # warm-up of the collective too (NCCL sets its channels up lazily)
+    torch.cuda.synchronize()
     eng.reset()
-    de, dc, dk = (torch.as_tensor(v, device=f"cuda:{local}") for v in eng.device_accumulators(0))
 
     # ---- timed region: K steps + the one all-reduce of the bins ----------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None

@@ -459,12 +459,17 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   CK(cudaFuncGetAttributes(&fattr, pick_propagate(d->cell_kind, true, true)));
   const size_t per_block = (size_t)prop.sharedMemPerMultiprocessor / D.blocks_per_sm - (size_t)prop.reservedSharedMemPerBlock - fattr.sharedSizeBytes;
   D.smem_block = std::min(per_block, (size_t)prop.sharedMemPerBlockOptin - fattr.sharedSizeBytes) / 16 * 16;
+  // Leave part of the SM's 256 KB to L1: the kernel runs at 128 registers per thread and the few values it spills
+  // around the inlined event bodies must hit L1 (measured on one box: 1568 slots with 28 KB of L1 1.66e9 phonons/s,
+  // 1280 slots with 60 KB 1.99e9).  The carve-out steps are 132 / 164 / 196 / 228 KB.
+  const size_t smem_cap = (size_t)std::max(16, env_int("R3D_SMEM_KB", 196)) * 1024 / D.blocks_per_sm - (size_t)prop.reservedSharedMemPerBlock - fattr.sharedSizeBytes;
+  D.smem_block = std::min(D.smem_block, smem_cap / 16 * 16);
   const uint32_t tb = Tab<true>::bytes(d->n_cells, d->cell_nparam, d->faces_per_cell, d->n_scat);
   D.table_bytes = ((size_t)nc * d->cell_nparam * 8 + (size_t)ns * 80 <= (size_t)env_int("R3D_SMALL_TABLE_BYTES", 24 * 1024)) ? tb : 0u;
   const size_t for_slots = D.smem_block - D.table_bytes;
   D.max_slots[0] = (uint32_t)std::min<size_t>(for_slots / R3D_SLOT_BYTES / 32 * 32, 65504);
   D.max_slots[1] = (uint32_t)std::min<size_t>(for_slots / R3D_SLOT_BYTES_TRACE / 32 * 32, 65504);
-  if (int cap = env_int("R3D_SLOTS_PER_BLOCK", 0)) {
+  if (int cap = env_int("R3D_SLOTS_PER_BLOCK", 1280)) {
     for (int t = 0; t < 2; t++) D.max_slots[t] = std::max(32u, std::min(D.max_slots[t], (uint32_t)cap / 32 * 32));
   }
   if (D.max_slots[1] < 32) return fail(R3D_EUNSUPPORTED, "shared memory too small for the phonon slots");
