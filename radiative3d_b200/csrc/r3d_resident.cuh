@@ -81,8 +81,8 @@ struct Tally {
 // ---- the slots (phonons.hpp:69-126): struct of arrays in shared memory, 16-byte elements where fields travel
 // together.  Every accessor derives its address from the CTA's dynamic shared-memory symbol, so the compiler emits
 // LDS / STS (pointers kept in a struct were treated as generic and cost a long-scoreboard wait per access).
-#define R3D_SLOT_BYTES 144u
-#define R3D_SLOT_BYTES_TRACE 156u
+#define R3D_SLOT_BYTES 146u
+#define R3D_SLOT_BYTES_TRACE 158u
 extern __shared__ __align__(16) unsigned char r3d_smem[];
 template <bool TRACE>
 struct Slots {
@@ -104,13 +104,14 @@ struct Slots {
   R3D_DEV uint32_t &tr(int which, uint32_t s) const { return reinterpret_cast<uint32_t *>(r3d_smem + (size_t)S * 136 + table_bytes)[(uint32_t)which * S + s]; }
   // queues of slot indices: buffer 0 / 1 = [cur|next] ready-to-advance slots from the front, free slots from the back;
   // buffer 2 = table draws: scatter draws from the front, source draws from the back; buffer 3 = face events: P from
-  // the front, S from the back
+  // the front, S from the back; buffer 4 = plain ray bending at a face (no catch, no R/T solve)
   R3D_DEV uint16_t *queue(uint32_t buf) const {
     return reinterpret_cast<uint16_t *>(r3d_smem + (size_t)S * (TRACE ? 148 : 136) + table_bytes) + (size_t)buf * S;
   }
 };
 
-// counters of the queues: cnt[0..3] = {advance, free} x {buffer 0, buffer 1}; cnt[4..7] = scatter draws, source draws, P faces, S faces
+// counters of the queues: cnt[0..3] = {advance, free} x {buffer 0, buffer 1}; cnt[4..8] = scatter draws, source draws, P faces,
+// S faces, bends
 // per-CTA clocks written at the end of a launch: [0] cycles in phase 1, [1] cycles in phase 2, [2] iterations,
 // [3..6] warp-cycles inside advance / refill / face / draw chunks, [7..10] number of such chunks, [11] warp-cycles
 // spent outside chunks (barriers, waiting for the last chunk of a phase)
@@ -120,11 +121,11 @@ struct Ctl {
   uint32_t n_kind[4];
   unsigned long long base;          // first phonon (relative to the job) granted to this CTA in this iteration
   uint32_t granted, exhausted, done, cursor[2];
-  uint32_t cnt[8];
+  uint32_t cnt[9];
   unsigned long long t_phase[2];    // clock cycles spent in phase 1 / phase 2 (thread 0's view)
   uint32_t iterations;
 };
-enum { CNT_SCAT = 4, CNT_SRC, CNT_FP, CNT_FS };
+enum { CNT_SCAT = 4, CNT_SRC, CNT_FP, CNT_FS, CNT_BEND };
 
 // ---- the small per-model tables every event reads: cell parameters, cell -> scatterer, face flags and neighbours,
 // mean free paths, conversion probabilities.  Layered and shell models have tens of cells (a few KB): SMALL stages
@@ -304,7 +305,7 @@ R3D_DEV void refraction_bend(const DevModel &M, const TabT &tab, Phonon &p, int 
 }
 
 // kinds of follow-up work a slot can be queued for
-enum { OUT_NONE = -1, OUT_ADV = 0, OUT_FREE, OUT_SCAT, OUT_SRC, OUT_FP, OUT_FS };
+enum { OUT_NONE = -1, OUT_ADV = 0, OUT_FREE, OUT_SCAT, OUT_SRC, OUT_FP, OUT_FS, OUT_BEND };
 
 // Append this lane's slot to the queue of its follow-up kind: lanes of one kind find each other with one match.any,
 // their leader reserves room with one shared-memory atomic.  All lanes of the warp call this.
@@ -319,7 +320,7 @@ R3D_DEV void route(const Slots<TRACE> &A, Ctl &C, int nxt, int out, uint32_t s) 
   if ((int)lane == leader) base = atomicAdd(&C.cnt[ci], (uint32_t)__popc(peers));
   base = __shfl_sync(peers, base, leader);
   const uint32_t j = base + __popc(peers & ((1u << lane) - 1u));
-  const uint32_t buf = (out < 2) ? (uint32_t)nxt : 1u + ((uint32_t)out >> 1);
+  const uint32_t buf = (out < 2) ? (uint32_t)nxt : 1u + ((uint32_t)out >> 1);       // OUT_BEND = 6 -> buffer 4, from the front
   A.queue(buf)[(out & 1) ? A.S - 1u - j : j] = (uint16_t)s;
 }
 
@@ -425,7 +426,7 @@ R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
         // collection and / or R/T and / or bending: phase 2.  For P only the outcome draw exists (k1).
         const uint32_t ka = (p.type == R3D_RAY_S) ? k1 : 0u, kb = (p.type == R3D_RAY_S) ? k2 : k1;
         A.req(s) = make_uint2(ka | ((uint32_t)(P.face & 1) << 31), kb | ((uint32_t)(P.face >> 1) << 31));
-        out = (p.type == R3D_RAY_P) ? OUT_FP : OUT_FS;
+        out = (action == FACE_BEND && !(fl & R3D_FACE_COLLECT)) ? OUT_BEND : (p.type == R3D_RAY_P) ? OUT_FP : OUT_FS;
       }
     }
   }
@@ -666,6 +667,28 @@ R3D_DEV int face_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, con
   return OUT_ADV;
 }
 
+// phase 2c: Snell bending at a face that neither collects nor reflects (phonons.cpp:311-405).  Layered models with
+// velocity contrasts cross such a face in half of their events; queued apart so that these cheap events do not sit in
+// the same warps as R/T solves.
+template <class Cell, bool TRACE, class TabT>
+R3D_DEV void bend_one(const DevModel &M, const Slots<TRACE> &A, const TabT &tab, uint32_t s) {
+  Phonon p;
+  const double2 lxy = A.lxy(s), lzdz = A.lzdz(s), dxy = A.dxy(s), sxy = A.sxy(s);
+  const uint4 meta = A.meta(s);
+  const uint2 q = A.req(s);
+  p.loc = V(lxy.x, lxy.y, lzdz.x);
+  p.dir = V(dxy.x, dxy.y, lzdz.y);
+  p.s1 = V(sxy.x, sxy.y, A.sz(s));
+  p.cell = meta.y; p.type = (int)meta.w;
+  const int face = (int)((q.x >> 31) | ((q.y >> 31) << 1));
+  refraction_bend<Cell>(M, tab, p, face, tab.other(M, p.cell * M.faces_per_cell + face));
+  A.dxy(s) = make_double2(p.dir.x, p.dir.y);
+  A.lzdz(s).y = p.dir.z;
+  A.sxy(s) = make_double2(p.s1.x, p.s1.y);
+  A.sz(s) = p.s1.z;
+  A.meta(s).y = p.cell;
+}
+
 // =====================================================================================================
 // the kernel: persistent CTAs, S slots each
 // =====================================================================================================
@@ -681,7 +704,7 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
   for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) A.queue(0)[S - 1u - i] = (uint16_t)i;     // every slot starts free
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) C.cnt[k] = 0;
+    for (int k = 0; k < 9; k++) C.cnt[k] = 0;
     C.cnt[OUT_FREE] = S;
     C.exhausted = 0; C.done = 0; C.t_phase[0] = 0; C.t_phase[1] = 0; C.iterations = 0;
     for (int k = 0; k < 4; k++) { C.t_kind[k] = 0; C.n_kind[k] = 0; }
@@ -707,7 +730,7 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
       }
       C.granted = grant;
       C.cnt[nxt * 2 + OUT_ADV] = 0; C.cnt[nxt * 2 + OUT_FREE] = 0;
-      C.cnt[CNT_SCAT] = 0; C.cnt[CNT_SRC] = 0; C.cnt[CNT_FP] = 0; C.cnt[CNT_FS] = 0;
+      C.cnt[CNT_SCAT] = 0; C.cnt[CNT_SRC] = 0; C.cnt[CNT_FP] = 0; C.cnt[CNT_FS] = 0; C.cnt[CNT_BEND] = 0;
       C.cursor[0] = 0; C.cursor[1] = 0;
       C.done = (C.cnt[cur * 2 + OUT_ADV] == 0 && grant == 0);
       t0 = clock64();
@@ -741,17 +764,25 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
     __syncthreads();
     if (threadIdx.x == 0) { const long long t1 = clock64(); C.t_phase[0] += (unsigned long long)(t1 - t0); t0 = t1; }
 
-    // ---- phase 2: face chunks (S, then P), then draw chunks (scatter, then source) -----------------------------
+    // ---- phase 2: face chunks (S, then P), then draw chunks (scatter, then source), then bend chunks ---------------
     {
       const uint32_t nFS = C.cnt[CNT_FS], nFP = C.cnt[CNT_FP], nDS = C.cnt[CNT_SCAT], nDR = C.cnt[CNT_SRC];
       constexpr uint32_t DB = 32u * R3D_DRAW_U;                 // draws per chunk
+      const uint32_t nB = C.cnt[CNT_BEND];
       const uint32_t c0 = (nFS + 31u) >> 5, c1 = c0 + ((nFP + 31u) >> 5), c2 = c1 + (nDS + DB - 1u) / DB, c3 = c2 + (nDR + DB - 1u) / DB;
-      const uint16_t *qd = A.queue(2), *qf = A.queue(3);
+      const uint32_t c4 = c3 + ((nB + 31u) >> 5);
+      const uint16_t *qd = A.queue(2), *qf = A.queue(3), *qb = A.queue(4);
       for (;;) {
         const uint32_t c = next_chunk(&C.cursor[1]);
-        if (c >= c3) break;
+        if (c >= c4) break;
         const long long tc = clock64();
-        if (c < c1) {
+        if (c >= c3) {
+          const uint32_t j = (c - c3) * 32u + lane;
+          int out = OUT_NONE;
+          uint32_t s = 0;
+          if (j < nB) { s = qb[j]; bend_one<Cell, TRACE>(M, A, tab, s); out = OUT_ADV; }
+          route<TRACE>(A, C, nxt, out, s);
+        } else if (c < c1) {
           const bool from_back = c < c0;
           const uint32_t j = (from_back ? c : c - c0) * 32u + lane, count = from_back ? nFS : nFP;
           int out = OUT_NONE;
@@ -766,7 +797,7 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
 #pragma unroll
           for (int u = 0; u < R3D_DRAW_U; u++) route<TRACE>(A, C, nxt, have[u] ? OUT_ADV : OUT_NONE, s[u]);
         }
-        if (lane == 0) { const int kd = (c < c1) ? 2 : 3; atomicAdd(&C.t_kind[kd], (unsigned long long)(clock64() - tc)); atomicAdd(&C.n_kind[kd], 1u); }
+        if (lane == 0) { const int kd = (c < c1 || c >= c3) ? 2 : 3; atomicAdd(&C.t_kind[kd], (unsigned long long)(clock64() - tc)); atomicAdd(&C.n_kind[kd], 1u); }
       }
     }
     __syncthreads();
