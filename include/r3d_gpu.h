@@ -180,6 +180,33 @@ typedef struct r3d_phonon_final {
   uint32_t iters;      /* loop iterations                             */
 } r3d_phonon_final;
 
+/* ---- event reports (reference DataReporter::Report*, dataout.cpp:484-617) ----
+ * One record per reported event, holding what output_phonon_dataline() prints: the phonon's state at the moment the
+ * reference would call the matching Report* method (phonons.cpp:540-682, events.cpp:120). */
+#define R3D_EV_GEN 0   /* "GEN: " new event phonon              (ReportNewEventPhonon) */
+#define R3D_EV_SCT 1   /* "SCT: " after a scatter's Transform   (ReportScatterEvent)   */
+#define R3D_EV_COL 2   /* "COL: " arrival at a collection face  (ReportPhononCollected)*/
+#define R3D_EV_REF 3   /* "REF: " reflected at a face           (ReportReflection)     */
+#define R3D_EV_CEL 4   /* "CEL: " crossed into another cell     (ReportCellToCell)     */
+#define R3D_EV_LST 5   /* "LST: " left the model                (ReportLostPhonon)     */
+#define R3D_EV_TMO 6   /* "TMO: " timed out                     (ReportPhononTimeout)  */
+#define R3D_EV_INV 7   /* "INV: " failed a validity check       (ReportInvalidPhonon)  */
+#define R3D_EV_ALL 0xFFu
+
+typedef struct r3d_event {
+  uint64_t phonon;     /* global phonon index                                   */
+  uint32_t seq;        /* ordinal of this report within its phonon (0, 1, ...)  */
+  uint32_t kind;       /* R3D_EV_*                                              */
+  uint32_t type;       /* R3D_RAY_P / R3D_RAY_S                                 */
+  uint32_t moves;      /* Phonon::mMoveCount ("it:")                            */
+  uint32_t cell;       /* cell index (the reference prints the cell's address)  */
+  uint32_t reserved;
+  double   time, pathlen;
+  double   loc[3];     /* model coordinates (the host applies ECS.OutConvert)   */
+  double   theta, phi;
+  double   amp;
+} r3d_event;
+
 typedef struct r3d_handle r3d_handle;
 
 /* Upload a model to `n_dev` CUDA devices (replicated) and allocate
@@ -239,6 +266,13 @@ int r3d_kernel_times(r3d_handle *h, double seconds[3], uint64_t launches[3], uin
  * phonon's end state to out[n] (host memory). */
 int r3d_trace(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons,
               uint64_t seed, r3d_phonon_final *out);
+
+/* Event reports for video runs: trace phonons [first, first+n) on device slot 0 (bins and counters accumulate as in
+ * r3d_run) and return the events whose kind is in kinds_mask (bit R3D_EV_*), sorted by (phonon, seq) - the order in which
+ * the single-threaded reference writes them.  At most `capacity` records are written to out; *n_events receives the number
+ * of events that occurred (if it exceeds capacity, call again with a larger buffer or a shorter range). */
+int r3d_trace_events(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons, uint64_t seed, uint32_t kinds_mask,
+                     r3d_event *out, uint64_t capacity, uint64_t *n_events);
 
 /* ---- deterministic sub-kernel hooks (parity at 1e-10) ----------
  * Each evaluates n independent cases on the device with the same device

@@ -13,6 +13,12 @@
 //     flatten model -> r3d_create -> r3d_run (10 slices, for the progress lines) -> r3d_fetch
 //     -> write bins / counters back into Seismometer / DataReporter objects
 //
+// Event reports (--reports=..., dataout.cpp:484-617): when any kind other than INV is switched on, the phonons are traced
+// in batches through r3d_trace_events() and every record is printed by the reference's own DataReporter::Report* methods
+// (hence its own output_phonon_dataline(): same line layout; the SID column holds the phonon index, and events come out
+// phonon by phonon as in the reference).  Their side effects - the seismometer scan of ReportPhononCollected and the
+// loss counters - are switched off around the printing, because the GPU already did both.
+//
 // Environment (all optional):
 //   R3D_GPU_DEVICES=0,1,...   CUDA devices to shard the phonon index range over   (default: 0)
 //   R3D_GPU_SEED=<u64>        Philox seed (default: time(NULL), like the reference's srand(time(NULL)))
@@ -84,8 +90,64 @@ void Model::RunSimulation() {
 
   std::cout << "@@ __BEGINNING_SIMULATION__" << std::endl << std::flush;
 
+  // which event reports does the user want?  (INV alone is what waveform runs use: nothing to print unless it happens)
+  uint32_t ev_mask = 0;
+  if (dataout.mbReportGenerate) ev_mask |= 1u << R3D_EV_GEN;
+  if (dataout.mbReportScatter)  ev_mask |= 1u << R3D_EV_SCT;
+  if (dataout.mbReportCollect)  ev_mask |= 1u << R3D_EV_COL;
+  if (dataout.mbReportReflect)  ev_mask |= 1u << R3D_EV_REF;
+  if (dataout.mbReportTransfer) ev_mask |= 1u << R3D_EV_CEL;
+  if (dataout.mbReportLost)     ev_mask |= 1u << R3D_EV_LST;
+  if (dataout.mbReportTimeout)  ev_mask |= 1u << R3D_EV_TMO;
+  if (dataout.mbReportInvalid)  ev_mask |= 1u << R3D_EV_INV;
+  const bool reporting = (ev_mask & ~(1u << R3D_EV_INV)) != 0;
+
   // ten slices so that the progress lines of model.cpp:616-628 keep appearing
   double device_seconds = 0;
+  if (reporting) {
+    // video runs: tens of thousands of phonons, every event printed
+    std::vector<Seismometer*> seis_keep;
+    seis_keep.swap(dataout.mSeismometers);                 // ReportPhononCollected must only print
+    const unsigned long keep_lost = dataout.mNumLost, keep_tmo = dataout.mNumTimeout, keep_inv = dataout.mNumInvalid;
+    const unsigned keep_diag = dataout.mDiagInvalid;
+    const uint64_t batch = 4096;
+    std::vector<r3d_event> ev(batch * 256);
+    Phonon P(S2::ThetaPhi(0, 0), RAY_P);
+    for (uint64_t lo = 0; lo < nph; lo += batch) {
+      const uint64_t n = std::min<uint64_t>(batch, nph - lo);
+      uint64_t got = 0;
+      for (;;) {
+        int rc = r3d_trace_events(h, lo, n, seed, ev_mask, ev.data(), ev.size(), &got);
+        if (rc != 0) { std::string msg = r3d_last_error(); r3d_destroy(h); throw Runtime("GPU propagate path: " + msg); }
+        if (got <= ev.size()) break;
+        r3d_destroy(h);
+        throw Runtime("GPU propagate path: more than 256 events per phonon on average; shorten --timetolive for report runs");
+      }
+      for (uint64_t i = 0; i < got; i++) {
+        const r3d_event & e = ev[i];
+        P.mSID = e.phonon;
+        P.mType = (e.type == R3D_RAY_P) ? RAY_P : RAY_S;
+        P.mTimeAlive = e.time; P.mPathLength = e.pathlen; P.mAmplitude = e.amp;
+        P.mLoc = R3::XYZ(e.loc[0], e.loc[1], e.loc[2]);
+        P.mDir = S2::ThetaPhi(e.theta, e.phi);
+        P.mpCell = mCellArray[e.cell];
+        P.mMoveCount = e.moves;
+        switch (e.kind) {
+          case R3D_EV_GEN: dataout.ReportNewEventPhonon(P); break;
+          case R3D_EV_SCT: dataout.ReportScatterEvent(P); break;
+          case R3D_EV_COL: dataout.ReportPhononCollected(P); break;
+          case R3D_EV_REF: dataout.ReportReflection(P); break;
+          case R3D_EV_CEL: dataout.ReportCellToCell(P); break;
+          case R3D_EV_LST: dataout.ReportLostPhonon(P); break;
+          case R3D_EV_TMO: dataout.ReportPhononTimeout(P); break;
+          default:         dataout.ReportInvalidPhonon(P, DataReporter::INV_PATH_NAN); break;
+        }
+      }
+      std::cerr << (100 * (lo + n)) / nph << "% of " << nph << " have been cast.\n";
+    }
+    seis_keep.swap(dataout.mSeismometers);
+    dataout.mNumLost = keep_lost; dataout.mNumTimeout = keep_tmo; dataout.mNumInvalid = keep_inv; dataout.mDiagInvalid = keep_diag;
+  } else
   for (int slice = 0; slice < 10; slice++) {
     uint64_t lo = nph / 10 * slice + (nph % 10) * slice / 10;
     uint64_t hi = nph / 10 * (slice + 1) + (nph % 10) * (slice + 1) / 10;
@@ -96,7 +158,7 @@ void Model::RunSimulation() {
     if (rc != 0) { std::string msg = r3d_last_error(); r3d_destroy(h); throw Runtime("GPU propagate path: " + msg); }
     device_seconds += t;
   }
-  std::cerr << "100% of " << nph << " have been cast.\n";
+  if (!reporting) std::cerr << "100% of " << nph << " have been cast.\n";
   std::cout << "@@ __SIMULATION_COMPLETE__" << std::endl;
 
   // bins and counters back into the reference's own objects

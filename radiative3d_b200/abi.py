@@ -72,5 +72,17 @@ PHONON_FINAL_DTYPE = np.dtype([
 assert PHONON_FINAL_DTYPE.itemsize == C.sizeof(PhononFinal) == 104
 
 
+R3D_EV_GEN, R3D_EV_SCT, R3D_EV_COL, R3D_EV_REF, R3D_EV_CEL, R3D_EV_LST, R3D_EV_TMO, R3D_EV_INV = range(8)
+R3D_EV_ALL = 0xFF
+EVENT_LABELS = ("GEN", "SCT", "COL", "REF", "CEL", "LST", "TMO", "INV")      # dataout.hpp:308-324
+
+# struct r3d_event
+EVENT_DTYPE = np.dtype([
+    ("phonon", "<u8"), ("seq", "<u4"), ("kind", "<u4"), ("type", "<u4"), ("moves", "<u4"), ("cell", "<u4"), ("reserved", "<u4"),
+    ("time", "<f8"), ("pathlen", "<f8"), ("loc", "<f8", (3,)), ("theta", "<f8"), ("phi", "<f8"), ("amp", "<f8"),
+])
+assert EVENT_DTYPE.itemsize == 96
+
+
 def as_ptr(a, ctype):
     return a.ctypes.data_as(C.POINTER(ctype))

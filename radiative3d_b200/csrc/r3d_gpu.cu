@@ -167,7 +167,11 @@ __global__ void test_catch_kernel(double bin_dt, uint32_t n_bins, const double *
 // ---------------------------------------------------------------------------
 // host side of the handle
 // ---------------------------------------------------------------------------
-struct JobReq { unsigned long long first, n, seed; r3d_phonon_final *finals; };
+struct JobReq {
+  unsigned long long first, n, seed;
+  r3d_phonon_final *finals;
+  r3d_event *events; unsigned long long *event_cursor, event_cap; uint32_t event_mask;
+};
 
 struct DevState {
   int device = -1;
@@ -497,8 +501,9 @@ int run_job(DevState &D, const JobReq &jr) {
   CK(cudaEventCreate(&ek1));
   CK(cudaEventRecord(ev0, D.stream));
   if (jr.n) {
-    const bool trace = jr.finals != nullptr;
+    const bool trace = jr.finals != nullptr || jr.events != nullptr;
     Job J; J.first = jr.first; J.n = jr.n; J.seed = jr.seed; J.finals = jr.finals;
+    J.events = jr.events; J.event_cursor = jr.event_cursor; J.event_cap = jr.event_cap; J.event_mask = jr.event_mask;
     // no more slots than phonons: a small job is spread over all CTAs instead of filling the first few
     uint32_t S = D.max_slots[trace ? 1 : 0];
     const unsigned long long share = (jr.n + (unsigned long long)D.grid - 1) / (unsigned long long)D.grid;
@@ -636,7 +641,7 @@ int r3d_run(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons, uint64_t s
   for (uint64_t g = 0; g < G; g++) {      // contiguous index ranges
     uint64_t lo = n_phonons / G * g + (n_phonons % G) * g / G;
     uint64_t hi = n_phonons / G * (g + 1) + (n_phonons % G) * (g + 1) / G;
-    JobReq jr; jr.first = first_phonon + lo; jr.n = hi - lo; jr.seed = seed; jr.finals = nullptr;
+    JobReq jr{}; jr.first = first_phonon + lo; jr.n = hi - lo; jr.seed = seed;
     enqueue(*h->devs[g], jr);
   }
   return 0;
@@ -789,7 +794,7 @@ int r3d_trace(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons, uint64_t
   CK(cudaSetDevice(D.device));
   r3d_phonon_final *dfin = nullptr;
   CK(cudaMalloc(&dfin, n_phonons * sizeof(r3d_phonon_final)));
-  JobReq jr; jr.first = first_phonon; jr.n = n_phonons; jr.seed = seed; jr.finals = dfin;
+  JobReq jr{}; jr.first = first_phonon; jr.n = n_phonons; jr.seed = seed; jr.finals = dfin;
   enqueue(D, jr);
   int rc = drain(D);
   cudaError_t e = cudaSuccess;
@@ -797,6 +802,36 @@ int r3d_trace(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons, uint64_t
   cudaFree(dfin);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(R3D_ECUDA, std::string("r3d_trace: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int r3d_trace_events(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons, uint64_t seed, uint32_t kinds_mask,
+                     r3d_event *out, uint64_t capacity, uint64_t *n_events) {
+  if (!h || !n_events || (capacity && !out)) return fail(R3D_EINVAL, "null argument");
+  *n_events = 0;
+  if (!n_phonons) return 0;
+  DevState &D = *h->devs[0];
+  if (int rc = drain(D)) return rc;
+  CK(cudaSetDevice(D.device));
+  r3d_event *dev = nullptr;
+  unsigned long long *cursor = nullptr;
+  CK(cudaMalloc(&dev, std::max<uint64_t>(capacity, 1) * sizeof(r3d_event)));
+  cudaError_t e = cudaMalloc(&cursor, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(cursor, 0, sizeof(unsigned long long));
+  if (e != cudaSuccess) { cudaFree(dev); cudaFree(cursor); return fail(R3D_ECUDA, std::string("r3d_trace_events: ") + cudaGetErrorString(e)); }
+  JobReq jr{}; jr.first = first_phonon; jr.n = n_phonons; jr.seed = seed;
+  jr.events = dev; jr.event_cursor = cursor; jr.event_cap = capacity; jr.event_mask = kinds_mask;
+  enqueue(D, jr);
+  int rc = drain(D);
+  unsigned long long total = 0;
+  if (!rc) e = cudaMemcpy(&total, cursor, sizeof total, cudaMemcpyDeviceToHost);
+  const uint64_t got = std::min<uint64_t>(total, capacity);
+  if (!rc && e == cudaSuccess && got) e = cudaMemcpy(out, dev, got * sizeof(r3d_event), cudaMemcpyDeviceToHost);
+  cudaFree(dev); cudaFree(cursor);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(R3D_ECUDA, std::string("r3d_trace_events: ") + cudaGetErrorString(e));
+  std::sort(out, out + got, [](const r3d_event &a, const r3d_event &b) { return a.phonon != b.phonon ? a.phonon < b.phonon : a.seq < b.seq; });
+  *n_events = total;
   return 0;
 }
 

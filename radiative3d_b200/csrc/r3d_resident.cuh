@@ -35,7 +35,13 @@ namespace r3d {
 #define R3D_MINBLOCKS 1        // 512 x 1 => 128 registers per thread; 256 threads x 2 CTAs per SM uses the same budget
 #endif
 
-struct Job { unsigned long long first, n, seed; r3d_phonon_final *finals; };
+struct Job {
+  unsigned long long first, n, seed;
+  r3d_phonon_final *finals;                  // trace mode: per-phonon end states (or null)
+  r3d_event *events;                         // trace mode: event reports (or null)
+  unsigned long long *event_cursor, event_cap;
+  uint32_t event_mask;
+};
 
 struct Phonon {
   double time, pathlen, recent, aexp;
@@ -82,7 +88,7 @@ struct Tally {
 // together.  Every accessor derives its address from the CTA's dynamic shared-memory symbol, so the compiler emits
 // LDS / STS (pointers kept in a struct were treated as generic and cost a long-scoreboard wait per access).
 #define R3D_SLOT_BYTES 146u
-#define R3D_SLOT_BYTES_TRACE 158u
+#define R3D_SLOT_BYTES_TRACE 162u
 extern __shared__ __align__(16) unsigned char r3d_smem[];
 template <bool TRACE>
 struct Slots {
@@ -100,13 +106,13 @@ struct Slots {
   // outcome choice}, exit face id in the two top bits
   R3D_DEV uint2 &req(uint32_t s) const { return reinterpret_cast<uint2 *>(r3d_smem + (size_t)S * 128)[s]; }
   R3D_DEV unsigned char *tables() const { return r3d_smem + (size_t)S * 136; }                                   // staged small-model tables (Tab)
-  // trace mode only: [3][S] catches, scatters, iterations
+  // trace mode only: [4][S] catches, scatters, iterations, event reports made
   R3D_DEV uint32_t &tr(int which, uint32_t s) const { return reinterpret_cast<uint32_t *>(r3d_smem + (size_t)S * 136 + table_bytes)[(uint32_t)which * S + s]; }
   // queues of slot indices: buffer 0 / 1 = [cur|next] ready-to-advance slots from the front, free slots from the back;
   // buffer 2 = table draws: scatter draws from the front, source draws from the back; buffer 3 = face events: P from
   // the front, S from the back; buffer 4 = plain ray bending at a face (no catch, no R/T solve)
   R3D_DEV uint16_t *queue(uint32_t buf) const {
-    return reinterpret_cast<uint16_t *>(r3d_smem + (size_t)S * (TRACE ? 148 : 136) + table_bytes) + (size_t)buf * S;
+    return reinterpret_cast<uint16_t *>(r3d_smem + (size_t)S * (TRACE ? 152 : 136) + table_bytes) + (size_t)buf * S;
   }
 };
 
@@ -204,7 +210,7 @@ R3D_DEV uint32_t next_chunk(uint32_t *cursor) {
 
 template <bool TRACE>
 R3D_DEV void write_final(const Slots<TRACE> &A, const Job &J, uint32_t s, const Phonon &p, uint32_t fate, uint32_t ordinal) {
-  if (!TRACE) return;
+  if (!TRACE || !J.finals) return;
   r3d_phonon_final *f = J.finals + (A.idx(s) - J.first);
   f->time = p.time; f->pathlen = p.pathlen; f->amp = exp(-p.aexp);
   f->loc[0] = p.loc.x; f->loc[1] = p.loc.y; f->loc[2] = p.loc.z;
@@ -212,6 +218,22 @@ R3D_DEV void write_final(const Slots<TRACE> &A, const Job &J, uint32_t s, const 
   f->pol = pol_angle_of(p.dir, p.s1);
   f->moves = p.moves; f->cell = p.cell; f->type = (uint32_t)p.type; f->fate = fate;
   f->draws = ordinal; f->catches = A.tr(0, s); f->scatters = A.tr(1, s); f->iters = A.tr(2, s);
+}
+
+// Event report (dataout.cpp:484-617): the phonon's state as output_phonon_dataline() prints it.  Trace mode only.
+template <bool TRACE>
+R3D_DEV void emit(const Slots<TRACE> &A, const Job &J, uint32_t s, uint32_t kind, int type, double time, double pathlen, v3 loc,
+                  v3 dir, double aexp, uint32_t cell, uint32_t moves) {
+  if (!TRACE) return;
+  if (!J.events || !((J.event_mask >> kind) & 1u)) return;
+  const uint32_t seq = A.tr(3, s)++;
+  const unsigned long long at = atomicAdd(J.event_cursor, 1ull);
+  if (at >= J.event_cap) return;
+  r3d_event *e = J.events + at;
+  e->phonon = A.idx(s); e->seq = seq; e->kind = kind; e->type = (uint32_t)type; e->moves = moves; e->cell = cell; e->reserved = 0;
+  e->time = time; e->pathlen = pathlen; e->loc[0] = loc.x; e->loc[1] = loc.y; e->loc[2] = loc.z;
+  angles_of(dir, e->theta, e->phi);
+  e->amp = exp(-aexp);
 }
 
 // one 32-byte take-off-angle record through the read-only path (two 16-byte loads of the same sector)
@@ -414,6 +436,7 @@ R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
           dir_changed = true;
           T.v[R3D_CNT_SCATTERS]++;
           if (TRACE) A.tr(1, s)++;
+          emit<TRACE>(A, J, s, R3D_EV_SCT, p.type, p.time, p.pathlen, p.loc, p.dir, p.aexp, p.cell, p.moves);
         } else {
           const uint32_t conv = cdf_search_small(tab.whole(M, scat, p.type), 4, k1);
           A.req(s) = make_uint2(k2, scat * 4 + conv);
@@ -421,7 +444,10 @@ R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
           out = OUT_SCAT;
         }
       } else if (action == FACE_LOST && !(fl & R3D_FACE_COLLECT)) fate = R3D_FATE_LOST;
-      else if (action == FACE_CONTINUOUS && !(fl & R3D_FACE_COLLECT)) p.cell = other;   // Refraction_Continuous
+      else if (action == FACE_CONTINUOUS && !(fl & R3D_FACE_COLLECT)) {                 // Refraction_Continuous
+        p.cell = other;
+        emit<TRACE>(A, J, s, (other == meta.y) ? R3D_EV_REF : R3D_EV_CEL, p.type, p.time, p.pathlen, p.loc, p.dir, p.aexp, p.cell, p.moves);
+      }
       else {
         // collection and / or R/T and / or bending: phase 2.  For P only the outcome draw exists (k1).
         const uint32_t ka = (p.type == R3D_RAY_S) ? k1 : 0u, kb = (p.type == R3D_RAY_S) ? k2 : k1;
@@ -434,6 +460,9 @@ R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
     T.died(fate);
     if (TRACE) {
       if (!s1_loaded) { const double2 sxy = A.sxy(s); p.s1 = V(sxy.x, sxy.y, A.sz(s)); }
+      const uint32_t f = fate & 0xFFu;
+      emit<TRACE>(A, J, s, f == R3D_FATE_LOST ? R3D_EV_LST : f == R3D_FATE_TIMEOUT ? R3D_EV_TMO : R3D_EV_INV, p.type, p.time, p.pathlen,
+                  p.loc, p.dir, p.aexp, p.cell, p.moves);
       write_final<TRACE>(A, J, s, p, fate, ordinal);
     }
     return OUT_FREE;
@@ -467,7 +496,7 @@ R3D_DEV void refill_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
   A.lzdz(s) = make_double2(M.src_loc[2], 0.0);
   A.idx(s) = idx;
   A.meta(s) = make_uint4(0u, M.src_cell, 2u, (rt3 == R3D_RAY_P) ? R3D_RAY_P : R3D_RAY_S);
-  if (TRACE) { A.tr(0, s) = 0; A.tr(1, s) = 0; A.tr(2, s) = 0; }
+  if (TRACE) { A.tr(0, s) = 0; A.tr(1, s) = 0; A.tr(2, s) = 0; A.tr(3, s) = 0; }
   T.v[6]++;
 }
 
@@ -482,7 +511,7 @@ R3D_DEV void refill_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
 #define R3D_DRAW_U 1
 #endif
 template <bool TRACE, int U>
-R3D_DEV void draw_batch(const DevModel &M, const Slots<TRACE> &A, const uint16_t *q, bool from_back, uint32_t j0, uint32_t count,
+R3D_DEV void draw_batch(const DevModel &M, const Job &J, const Slots<TRACE> &A, const uint16_t *q, bool from_back, uint32_t j0, uint32_t count,
                         bool is_src, Tally &T, uint32_t (&s)[U], bool (&have)[U]) {
   const unsigned lane = threadIdx.x & 31u;
   const double *cdf0 = is_src ? M.src_cdf : M.scat_cdf;
@@ -578,6 +607,11 @@ R3D_DEV void draw_batch(const DevModel &M, const Slots<TRACE> &A, const uint16_t
       A.lzdz(su).y = t[u].y;
       if (tbl[u] == R3D_RAY_SH) { A.sxy(su) = make_double2(-t[u].z, t[u].w); A.sz(su) = 0.0; }                     // phi-hat
       else { A.sxy(su) = make_double2(t[u].y * t[u].w, t[u].y * t[u].z); A.sz(su) = -t[u].x; }                     // theta-hat
+      if (TRACE && J.events) {             // events.cpp:120
+        const uint4 meta = A.meta(su);
+        emit<TRACE>(A, J, su, R3D_EV_GEN, (int)meta.w, 0.0, 0.0, V(M.src_loc[0], M.src_loc[1], M.src_loc[2]),
+                    V(t[u].x * t[u].w, t[u].x * t[u].z, t[u].y), 0.0, meta.y, 0u);
+      }
     } else {
       const uint32_t conv = tbl[u] & 3u;
       const double2 dxy = A.dxy(su), sxy = A.sxy(su);
@@ -590,6 +624,11 @@ R3D_DEV void draw_batch(const DevModel &M, const Slots<TRACE> &A, const uint16_t
       A.meta(su).w = conv & 1u;                               // PP,PS,SP,SS -> P,S,P,S
       T.v[R3D_CNT_SCATTERS]++;
       if (TRACE) A.tr(1, su)++;
+      if (TRACE && J.events) {             // phonons.cpp:616
+        const double2 tp = A.tp(su), ra = A.ra(su), lxy = A.lxy(su);
+        const uint4 meta = A.meta(su);
+        emit<TRACE>(A, J, su, R3D_EV_SCT, (int)(conv & 1u), tp.x, tp.y, V(lxy.x, lxy.y, A.lzdz(su).x), e3, ra.y, meta.y, meta.x);
+      }
     }
   }
 }
@@ -614,6 +653,7 @@ R3D_DEV int face_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, con
   const uint32_t fi = p.cell * M.faces_per_cell + face;
   const uint32_t fl = tab.flags(M, fi), other = tab.other(M, fi);
 
+  if (fl & R3D_FACE_COLLECT) emit<TRACE>(A, J, s, R3D_EV_COL, p.type, p.time, p.pathlen, p.loc, p.dir, p.aexp, p.cell, p.moves);
   // ---- collection (dataout.cpp:545-568): every seismometer is pass-through (dataout.cpp:50), so all that contain
   // the point must bin it.  Candidates come from the uniform grid over the seismometers' bounding spheres. --------
   if ((fl & R3D_FACE_COLLECT) && M.n_seis > 0) {
@@ -656,9 +696,13 @@ R3D_DEV int face_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, con
   else if (action == FACE_CONTINUOUS) p.cell = other;
   else {
     T.died(R3D_FATE_LOST);
+    emit<TRACE>(A, J, s, R3D_EV_LST, p.type, p.time, p.pathlen, p.loc, p.dir, p.aexp, p.cell, p.moves);
     write_final<TRACE>(A, J, s, p, R3D_FATE_LOST, meta.z);
     return OUT_FREE;
   }
+  // phonons.cpp:640-664: a reflection face always reports REF; a neighbour face REF if the cell is unchanged, else CEL
+  emit<TRACE>(A, J, s, ((fl & R3D_FACE_REFLECT) || p.cell == meta.y) ? R3D_EV_REF : R3D_EV_CEL, p.type, p.time, p.pathlen, p.loc, p.dir,
+              p.aexp, p.cell, p.moves);
   A.dxy(s) = make_double2(p.dir.x, p.dir.y);
   A.lzdz(s).y = p.dir.z;
   A.sxy(s) = make_double2(p.s1.x, p.s1.y);
@@ -671,7 +715,7 @@ R3D_DEV int face_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, con
 // velocity contrasts cross such a face in half of their events; queued apart so that these cheap events do not sit in
 // the same warps as R/T solves.
 template <class Cell, bool TRACE, class TabT>
-R3D_DEV void bend_one(const DevModel &M, const Slots<TRACE> &A, const TabT &tab, uint32_t s) {
+R3D_DEV void bend_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, const TabT &tab, uint32_t s) {
   Phonon p;
   const double2 lxy = A.lxy(s), lzdz = A.lzdz(s), dxy = A.dxy(s), sxy = A.sxy(s);
   const uint4 meta = A.meta(s);
@@ -687,6 +731,10 @@ R3D_DEV void bend_one(const DevModel &M, const Slots<TRACE> &A, const TabT &tab,
   A.sxy(s) = make_double2(p.s1.x, p.s1.y);
   A.sz(s) = p.s1.z;
   A.meta(s).y = p.cell;
+  if (TRACE && J.events) {
+    const double2 tp = A.tp(s), ra = A.ra(s);
+    emit<TRACE>(A, J, s, (p.cell == meta.y) ? R3D_EV_REF : R3D_EV_CEL, p.type, tp.x, tp.y, p.loc, p.dir, ra.y, p.cell, meta.x);
+  }
 }
 
 // =====================================================================================================
@@ -780,7 +828,7 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
           const uint32_t j = (c - c3) * 32u + lane;
           int out = OUT_NONE;
           uint32_t s = 0;
-          if (j < nB) { s = qb[j]; bend_one<Cell, TRACE>(M, A, tab, s); out = OUT_ADV; }
+          if (j < nB) { s = qb[j]; bend_one<Cell, TRACE>(M, J, A, tab, s); out = OUT_ADV; }
           route<TRACE>(A, C, nxt, out, s);
         } else if (c < c1) {
           const bool from_back = c < c0;
@@ -793,7 +841,7 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
           const bool is_src = c >= c2;
           uint32_t s[R3D_DRAW_U];
           bool have[R3D_DRAW_U];
-          draw_batch<TRACE, R3D_DRAW_U>(M, A, qd, is_src, (is_src ? c - c2 : c - c1) * DB, is_src ? nDR : nDS, is_src, T, s, have);
+          draw_batch<TRACE, R3D_DRAW_U>(M, J, A, qd, is_src, (is_src ? c - c2 : c - c1) * DB, is_src ? nDR : nDS, is_src, T, s, have);
 #pragma unroll
           for (int u = 0; u < R3D_DRAW_U; u++) route<TRACE>(A, C, nxt, have[u] ? OUT_ADV : OUT_NONE, s[u]);
         }

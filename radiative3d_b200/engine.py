@@ -21,7 +21,7 @@ _lib = None
 
 EXPORTS = [
     "r3d_create", "r3d_run", "r3d_sync", "r3d_fetch", "r3d_reset", "r3d_device_accumulators", "r3d_stream",
-    "r3d_launch_count", "r3d_trace", "r3d_set_profiling", "r3d_kernel_times", "r3d_test_cdf_search", "r3d_test_path_to_boundary", "r3d_test_advance",
+    "r3d_launch_count", "r3d_trace", "r3d_trace_events", "r3d_set_profiling", "r3d_kernel_times", "r3d_test_cdf_search", "r3d_test_path_to_boundary", "r3d_test_advance",
     "r3d_test_transform", "r3d_test_rtcoef", "r3d_test_catch", "r3d_destroy", "r3d_last_error", "r3d_abi_version",
 ]
 
@@ -55,6 +55,7 @@ def load_library(path=None):
     L.r3d_stream.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.r3d_launch_count.argtypes = [vp, pu64]
     L.r3d_trace.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
+    L.r3d_trace_events.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, vp, C.c_uint64, pu64]
     L.r3d_set_profiling.argtypes = [vp, C.c_int]
     L.r3d_kernel_times.argtypes = [vp, pd, pu64, pu64]
     L.r3d_test_cdf_search.argtypes = [pd, C.c_uint32, pu32, C.c_uint32, pu32, C.c_int]
@@ -151,6 +152,18 @@ class Engine:
         out = np.zeros(n_phonons, dtype=abi.PHONON_FINAL_DTYPE)
         _ck(self._L, self._L.r3d_trace(self._h, first_phonon, n_phonons, seed, out.ctypes.data))
         return out
+
+    def trace_events(self, n_phonons, seed=20261018, first_phonon=0, kinds=abi.R3D_EV_ALL, capacity=None):
+        """Event reports (DataReporter::Report*, dataout.cpp:484-617) of phonons [first, first+n), sorted by
+        (phonon, seq); also accumulates bins like run_simulation.  `capacity` = records to make room for
+        (default 512 per phonon); raises if more events occurred (the bins then hold this pass already)."""
+        cap = int(capacity or max(4096, 512 * n_phonons))
+        out = np.zeros(cap, dtype=abi.EVENT_DTYPE)
+        n = C.c_uint64()
+        _ck(self._L, self._L.r3d_trace_events(self._h, first_phonon, n_phonons, seed, kinds, out.ctypes.data, cap, C.byref(n)))
+        if n.value > cap:
+            raise R3DError(abi.R3D_EINVAL if hasattr(abi, "R3D_EINVAL") else 1, f"{n.value} events occurred, room for {cap}")
+        return out[:n.value]
 
     @property
     def launch_count(self):
