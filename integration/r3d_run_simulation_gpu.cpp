@@ -23,6 +23,11 @@
 //   R3D_GPU_DEVICES=0,1,...   CUDA devices to shard the phonon index range over   (default: 0)
 //   R3D_GPU_SEED=<u64>        Philox seed (default: time(NULL), like the reference's srand(time(NULL)))
 //   R3D_GPU_NUM_PHONONS=<u64> 64-bit phonon count, overrides --num-phonons (the reference's is an int)
+//   R3D_GPU_CHECKPOINT=<path> after every tenth of the run write bins + counters + the phonon-index watermark to <path>;
+//                             if <path> exists and belongs to the same run (count, seed, bin layout), continue from its
+//                             watermark.  Phonon i always uses draw stream (seed, i), so a resumed run equals an
+//                             uninterrupted one (the reference can only "resume" by adding another run, combine.m).
+//   R3D_GPU_STOP_AFTER=<k>    stop after k tenths (testing the checkpoint)
 //   R3D_GPU_DUMP_MODEL=<path> also write the flattened model (include/r3d_modelfile.h)
 //   R3D_GPU_DUMP_ONLY=1       ... and return without simulating
 #include <iostream>
@@ -56,6 +61,37 @@
 #include "r3d_flatten.hpp"
 
 namespace {
+// checkpoint file: header, then energies f64, counts u64, counters u64
+struct CkptHeader { char magic[8]; uint64_t nph, seed, watermark, n_seis, n_bins; };
+bool ckpt_read(const char * path, uint64_t nph, uint64_t seed, size_t ns, size_t nb, uint64_t & watermark,
+               std::vector<double> & e, std::vector<uint64_t> & c, std::vector<uint64_t> & k) {
+  FILE * f = fopen(path, "rb");
+  if (!f) return false;
+  CkptHeader hd;
+  bool ok = fread(&hd, sizeof hd, 1, f) == 1 && memcmp(hd.magic, "R3DCKPT1", 8) == 0 && hd.nph == nph && hd.seed == seed &&
+            hd.n_seis == ns && hd.n_bins == nb && hd.watermark <= nph;
+  ok = ok && fread(e.data(), sizeof(double), ns * nb * R3D_BIN_NF64, f) == ns * nb * R3D_BIN_NF64;
+  ok = ok && fread(c.data(), sizeof(uint64_t), ns * nb * R3D_BIN_NCNT, f) == ns * nb * R3D_BIN_NCNT;
+  ok = ok && fread(k.data(), sizeof(uint64_t), R3D_NCOUNTERS, f) == R3D_NCOUNTERS;
+  fclose(f);
+  if (ok) watermark = hd.watermark;
+  return ok;
+}
+void ckpt_write(const char * path, uint64_t nph, uint64_t seed, size_t ns, size_t nb, uint64_t watermark,
+                const std::vector<double> & e, const std::vector<uint64_t> & c, const std::vector<uint64_t> & k) {
+  std::string tmp = std::string(path) + ".tmp";
+  FILE * f = fopen(tmp.c_str(), "wb");
+  if (!f) throw Runtime(std::string("cannot write checkpoint ") + tmp);
+  CkptHeader hd;
+  memcpy(hd.magic, "R3DCKPT1", 8);
+  hd.nph = nph; hd.seed = seed; hd.watermark = watermark; hd.n_seis = ns; hd.n_bins = nb;
+  fwrite(&hd, sizeof hd, 1, f);
+  fwrite(e.data(), sizeof(double), ns * nb * R3D_BIN_NF64, f);
+  fwrite(c.data(), sizeof(uint64_t), ns * nb * R3D_BIN_NCNT, f);
+  fwrite(k.data(), sizeof(uint64_t), R3D_NCOUNTERS, f);
+  fclose(f);
+  rename(tmp.c_str(), path);                 // a checkpoint is either the old one or the new one, never half of one
+}
 void r3d_check(int rc, const char * what) {
   if (rc != 0)   // same convention as the rest of the program: user-facing failure -> Runtime (typedefs.hpp:123)
     throw Runtime(std::string("GPU propagate path: ") + what + ": " + r3d_last_error());
@@ -102,6 +138,10 @@ void Model::RunSimulation() {
   if (dataout.mbReportInvalid)  ev_mask |= 1u << R3D_EV_INV;
   const bool reporting = (ev_mask & ~(1u << R3D_EV_INV)) != 0;
 
+  const size_t ns = dataout.mSeismometers.size(), nb = Seismometer::cmNumBins;
+  std::vector<double> e0(ns * nb * R3D_BIN_NF64 + 1, 0.0);               // what a resumed run starts from
+  std::vector<uint64_t> c0(ns * nb * R3D_BIN_NCNT + 1, 0), k0(R3D_NCOUNTERS, 0);
+
   // ten slices so that the progress lines of model.cpp:616-628 keep appearing
   double device_seconds = 0;
   if (reporting) {
@@ -147,28 +187,55 @@ void Model::RunSimulation() {
     }
     seis_keep.swap(dataout.mSeismometers);
     dataout.mNumLost = keep_lost; dataout.mNumTimeout = keep_tmo; dataout.mNumInvalid = keep_inv; dataout.mDiagInvalid = keep_diag;
-  } else
+  } else {
+  const char * ckpt = getenv("R3D_GPU_CHECKPOINT");
+  const int stop_after = getenv("R3D_GPU_STOP_AFTER") ? atoi(getenv("R3D_GPU_STOP_AFTER")) : 10;
+  uint64_t watermark = 0;
+  if (ckpt && ckpt_read(ckpt, nph, seed, ns, nb, watermark, e0, c0, k0))
+    std::cerr << "r3d-gpu: resuming from checkpoint " << ckpt << " at phonon " << watermark << "\n";
+  else { std::fill(e0.begin(), e0.end(), 0.0); std::fill(c0.begin(), c0.end(), 0); std::fill(k0.begin(), k0.end(), 0); watermark = 0; }
   for (int slice = 0; slice < 10; slice++) {
     uint64_t lo = nph / 10 * slice + (nph % 10) * slice / 10;
     uint64_t hi = nph / 10 * (slice + 1) + (nph % 10) * (slice + 1) / 10;
     std::cerr << slice * 10 << "% of " << nph << " have been cast.\n";
+    if (hi <= watermark) continue;             // done before the interruption
+    if (lo < watermark) lo = watermark;
     int rc = r3d_run(h, lo, hi - lo, seed);
     double t = 0;
     if (rc == 0) rc = r3d_sync(h, &t);
     if (rc != 0) { std::string msg = r3d_last_error(); r3d_destroy(h); throw Runtime("GPU propagate path: " + msg); }
     device_seconds += t;
+    if (ckpt) {
+      std::vector<double> e(e0.size());
+      std::vector<uint64_t> c(c0.size()), k(R3D_NCOUNTERS);
+      uint32_t dg = 0;
+      r3d_check(r3d_fetch(h, e.data(), c.data(), k.data(), &dg), "r3d_fetch");
+      for (size_t i = 0; i < e.size(); i++) e[i] += e0[i];
+      for (size_t i = 0; i < c.size(); i++) c[i] += c0[i];
+      for (int i = 0; i < R3D_NCOUNTERS; i++) { if (i == 7) k[i] |= k0[i]; else k[i] += k0[i]; }
+      ckpt_write(ckpt, nph, seed, ns, nb, hi, e, c, k);
+    }
+    if (slice + 1 >= stop_after && slice + 1 < 10) {
+      std::cerr << "r3d-gpu: stopping after " << (slice + 1) << " tenths as asked (R3D_GPU_STOP_AFTER)\n";
+      r3d_destroy(h);
+      exit(3);
+    }
+  }
   }
   if (!reporting) std::cerr << "100% of " << nph << " have been cast.\n";
   std::cout << "@@ __SIMULATION_COMPLETE__" << std::endl;
 
   // bins and counters back into the reference's own objects
-  const size_t ns = dataout.mSeismometers.size(), nb = Seismometer::cmNumBins;
   std::vector<double> e(ns * nb * R3D_BIN_NF64 + 1);
   std::vector<uint64_t> c(ns * nb * R3D_BIN_NCNT + 1), k(R3D_NCOUNTERS);
   uint32_t diag = 0;
   int rc = r3d_fetch(h, e.data(), c.data(), k.data(), &diag);
   if (rc != 0) { std::string msg = r3d_last_error(); r3d_destroy(h); throw Runtime("GPU propagate path: " + msg); }
   r3d_destroy(h);
+  for (size_t i = 0; i < e.size(); i++) e[i] += e0[i];
+  for (size_t i = 0; i < c.size(); i++) c[i] += c0[i];
+  for (int i = 0; i < R3D_NCOUNTERS; i++) { if (i == 7) k[i] |= k0[i]; else k[i] += k0[i]; }
+  diag |= (uint32_t)k0[7];
   bool clipped = false;
   for (size_t s = 0; s < ns; s++) {
     Seismometer & S = *dataout.mSeismometers[s];

@@ -11,7 +11,7 @@ hdr = rows[1]
 ci, ct, cs = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("Warp Stall Sampling (All Samples)")
 inst = [(r[1].strip(), int(r[ci]), int(r[ct]), int(r[cs])) for r in rows[2:] if len(r) > ct]
 with tempfile.TemporaryDirectory() as tmp:
-    subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "radiative3d_b200", "libr3dgpu.so")], cwd=tmp, capture_output=True)
+    subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("R3D_PROFILE_LIB", os.path.join(ROOT, "radiative3d_b200", "libr3dgpu.so"))], cwd=tmp, capture_output=True)
     cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
     sass = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
 cands, lines, cur, grab = [], [], None, False

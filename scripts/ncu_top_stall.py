@@ -9,7 +9,7 @@ rows = list(csv.reader(io.StringIO(raw)))
 hdr = rows[1]; data = rows[2:]
 si, ci, ai = hdr.index(stall), hdr.index("Instructions Executed"), hdr.index("Avg. Threads Executed")
 with tempfile.TemporaryDirectory() as tmp:
-    subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "radiative3d_b200", "libr3dgpu.so")], cwd=tmp, capture_output=True)
+    subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("R3D_PROFILE_LIB", os.path.join(ROOT, "radiative3d_b200", "libr3dgpu.so"))], cwd=tmp, capture_output=True)
     cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
     sass = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
 cands, lines, cur, grab = [], [], None, False

@@ -33,14 +33,15 @@ def test_exports_every_declared_symbol():
 def test_struct_sizes_match_c(tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "r3d_gpu.h"\n#include "r3d_modelfile.h"\n'
-                   'int main(){printf("%zu %zu %zu\\n", sizeof(r3d_model_desc), sizeof(r3d_phonon_final),'
-                   ' sizeof(r3d_modelfile_scalars));return 0;}\n')
+                   'int main(){printf("%zu %zu %zu %zu\\n", sizeof(r3d_model_desc), sizeof(r3d_phonon_final),'
+                   ' sizeof(r3d_modelfile_scalars), sizeof(r3d_event));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
-    a, b, c = map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
+    a, b, c, d = map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
     assert a == C.sizeof(abi.ModelDesc)
     assert b == C.sizeof(abi.PhononFinal) == abi.PHONON_FINAL_DTYPE.itemsize
     assert c == 160
+    assert d == abi.EVENT_DTYPE.itemsize
 
 
 def test_abi_version():

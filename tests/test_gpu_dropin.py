@@ -51,3 +51,34 @@ def test_reference_program_with_gpu_loop(cfg, deg, n, tmp_path):
         assert np.allclose(o["TracePS"], e[i][:, 3:5], rtol=2e-5, atol=0)
         assert np.allclose(o["TraceXYZ"], e[i][:, 0:3], rtol=2e-5, atol=1e-300)
     assert os.path.exists(os.path.join(tmp_path, "seis_traces_asc.dat"))
+
+
+def test_checkpoint_and_resume(tmp_path):
+    """R3D_GPU_CHECKPOINT: a run stopped after 4 tenths and resumed equals the uninterrupted run (phonon i always uses
+    draw stream (seed, i)): counts and loss counters exactly, energies up to summation order."""
+    if not os.path.exists(reference_host.GPU_MAIN):
+        pytest.skip("integration/_build/r3d_gpu_main was not built (needs the reference checkout at build time)")
+    import subprocess
+    from radiative3d_b200 import workloads
+    cfg, deg, n, seed = "halfspace", 4, 400000, 99
+
+    def run(outdir, **extra):
+        os.makedirs(outdir, exist_ok=True)
+        env = dict(os.environ, R3D_GPU_SEED=str(seed), **extra)
+        return subprocess.run([reference_host.GPU_MAIN] + workloads.cmdline(cfg, n, deg, str(outdir)), cwd=str(outdir), env=env,
+                              capture_output=True, text=True)
+
+    whole = run(tmp_path / "whole")
+    assert whole.returncode == 0
+    ck = str(tmp_path / "run.ckpt")
+    part = run(tmp_path / "resumed", R3D_GPU_CHECKPOINT=ck, R3D_GPU_STOP_AFTER="4")
+    assert part.returncode == 3 and os.path.exists(ck)
+    rest = run(tmp_path / "resumed", R3D_GPU_CHECKPOINT=ck)
+    assert rest.returncode == 0 and "resuming from checkpoint" in rest.stderr
+    summary = lambda p: re.findall(r"(Loss surfaces|Timeout|Invalidity):\s+(\d+)", p.stdout)
+    assert summary(whole) == summary(rest)
+    for i in (0, 70, 143):
+        a = read_octv(os.path.join(tmp_path / "whole", f"seis_{i:03d}.octv"))
+        b = read_octv(os.path.join(tmp_path / "resumed", f"seis_{i:03d}.octv"))
+        assert np.array_equal(a["CountPS"], b["CountPS"])
+        assert np.allclose(a["TracePS"], b["TracePS"], rtol=1e-5, atol=0)
