@@ -151,3 +151,21 @@ def test_kernel_times_report():
     assert abs(kt["phase1_seconds"] + kt["phase2_seconds"] - kt["seconds"]) <= 1e-9 + 1e-6 * kt["seconds"]
     assert kt["events"] == int(k[abi.R3D_CNT_EVENTS]) and kt["catches"] == int(c.sum())
     assert kt["draws"] == int(k[abi.R3D_CNT_SCATTERS]) + 50000
+
+
+def test_two_devices_in_one_handle():
+    """r3d_create(devices[]) replicates the model and r3d_run shards the index range: the result equals the
+    single-device one (counts exactly, energies up to summation order)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    m, _ = load_golden("lopnor")
+    n = 30001
+    with engine.Engine(m, devices=(0,)) as eng:
+        eng.run_simulation(n, seed=21)
+        e1, c1, k1 = eng.fetch()
+    with engine.Engine(m, devices=(0, 1)) as eng:
+        eng.run_simulation(n, seed=21)
+        e2, c2, k2 = eng.fetch()
+    assert np.array_equal(c1, c2) and np.array_equal(k1[:7], k2[:7])
+    assert bin_energy_err(e1, e2) <= 1e-12
