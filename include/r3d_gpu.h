@@ -274,6 +274,22 @@ int r3d_trace(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons,
 int r3d_trace_events(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons, uint64_t seed, uint32_t kinds_mask,
                      r3d_event *out, uint64_t capacity, uint64_t *n_events);
 
+/* ---- scatterer tables: what the reference's Scatterer constructor computes -------------------------
+ * Scatterer::PopulateProbDists / PopulateWholeProbs / ComputeMFPs (scatterers.cpp:134-220) with
+ * ScatterParams::GSATO / XSATO / PSATO (scatparams.cpp:75-194, Sato & Fehler 4.50-4.52, von Karman PSDF): the G values of
+ * all take-off angles are evaluated on the device; the cumulative sums are then formed on the host in index order, as
+ * ProbDist::Integrate does (probability.cpp:21-35), because their rounding decides table indices.
+ * This is the model-build hot spot of the reference (0.3 s per scatterer at TOA degree 9, up to 28 scatterers). */
+typedef struct r3d_scatter_params {
+  double nu, eps, a, kappa;   /* density/velocity scaling, RMS perturbation, correlation distance, von Karman parameter */
+  double el, gam0;            /* S wavenumber omega / beta0, Vp / Vs                                                   */
+} r3d_scatter_params;
+/* For each of the n_par parameter sets: cdf[p][4][n_toa] (PP,PS,SP,SS, cumulative), spol[p][n_toa], whole_cdf[p][2][4]
+ * (cumulative, as r3d_model_desc.scat_whole_cdf), mfp[p][2]; all host arrays, laid out as r3d_model_desc wants them.
+ * The take-off angles are uploaded once; uses CUDA device `device`. */
+int r3d_build_scatterer_tables(const r3d_scatter_params *par, uint32_t n_par, const double *toa_theta, const double *toa_phi,
+                               uint32_t n_toa, int device, double *cdf, double *spol, double *whole_cdf, double *mfp);
+
 /* ---- deterministic sub-kernel hooks (parity at 1e-10) ----------
  * Each evaluates n independent cases on the device with the same device
  * functions the propagate kernel uses. */

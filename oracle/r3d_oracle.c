@@ -1019,3 +1019,56 @@ void r3d_oracle_catch(double bin_dt, uint32_t n_bins, const double *in, uint32_t
     o[0] = c; o[1] = c ? (double)bin : -1.0; o[2] = e[0]; o[3] = e[1]; o[4] = e[2]; o[5] = e[3];
   }
 }
+
+
+/* ===========================================================================
+ * Scatterer tables (scatterers.cpp:134-220, scatparams.cpp:75-194)
+ * ======================================================================== */
+static double psato(const r3d_scatter_params *P, double m) {            /* scatparams.cpp:181-194 */
+  const double pi32 = pow(3.14159265358979323846, 1.5);
+  const double numer = (8. * pi32 * P->eps * P->eps * P->a * P->a * P->a) * tgamma(P->kappa + 1.5) / tgamma(P->kappa);
+  const double denom = pow((1. + P->a * P->a * m * m), (P->kappa + 1.5));
+  return numer / denom;
+}
+void r3d_oracle_build_scatterer_tables(const r3d_scatter_params *P, const double *toa_theta, const double *toa_phi,
+                                       uint32_t n_toa, double *cdf, double *spol, double *whole_cdf, double *mfp) {
+  const size_t n = n_toa;
+  const double pi = 3.14159265358979323846;
+  for (size_t k = 0; k < n; k++) {
+    /* XSATO, scatparams.cpp:136-160 */
+    const double th = toa_theta[k], ph = toa_phi[k];
+    const double gam0 = P->gam0, nu = P->nu, el = P->el;
+    const double gam2x = gam0 * gam0;
+    const double cpsi = cos(th), c2psi = cos(2. * th), spsi = sin(th), czeta = cos(ph), szeta = sin(ph), spsi2 = spsi * spsi;
+    const double xpp = (1. / gam2x) * (nu * (-1. + cpsi + (2. / gam2x) * spsi2) - 2. + (4. / gam2x) * spsi2);
+    const double xps = -spsi * (nu * (1. - (2. / gam0) * cpsi) - (4. / gam0) * cpsi);
+    const double xsp = (1. / gam2x) * spsi * czeta * (nu * (1. - (2. / gam0) * cpsi) - (4. / gam0) * cpsi);
+    const double xss_psi = czeta * (nu * (cpsi - c2psi) - 2. * c2psi);
+    const double xss_zeta = szeta * (nu * (cpsi - 1.) + 2. * cpsi);
+    /* GSATO, scatparams.cpp:75-118 */
+    const double pi4 = 4. * pi, el4 = pow(el, 4), gam2 = pow(gam0, 2), psi = th;
+    double arg = (2. * el / gam0) * sin(psi / 2.);
+    double gpp = (el4 / pi4) * (xpp * xpp) * psato(P, arg);
+    if (gpp < 1.e-30) gpp = 0.;
+    arg = (el / gam0) * sqrt(1. + gam2 - 2. * gam0 * cos(psi));
+    double gps = (1. / gam0) * (el4 / pi4) * (xps * xps) * psato(P, arg);
+    if (gps < 1.e-30) gps = 0.;
+    double gsp = gam0 * (el4 / pi4) * (xsp * xsp) * psato(P, arg);
+    if (gsp < 1.e-30) gsp = 0.;
+    arg = 2. * el * sin(psi / 2.);
+    double gss = (el4 / pi4) * (xss_psi * xss_psi + xss_zeta * xss_zeta) * psato(P, arg);
+    if (gss < 1.e-30) gss = 0.;
+    cdf[k] = gpp; cdf[n + k] = gps; cdf[2 * n + k] = gsp; cdf[3 * n + k] = gss;
+    spol[k] = atan2(xss_zeta, xss_psi);
+  }
+  for (int t = 0; t < 4; t++) {            /* ProbDist::Integrate, probability.cpp:21-35 */
+    double *c = cdf + (size_t)t * n;
+    for (size_t i = 1; i < n; i++) c[i] += c[i - 1];
+  }
+  /* PopulateWholeProbs (scatterers.cpp:170-183), integrated */
+  whole_cdf[0] = cdf[n - 1]; whole_cdf[1] = whole_cdf[0] + cdf[2 * n - 1]; whole_cdf[2] = whole_cdf[1] + 0.0; whole_cdf[3] = whole_cdf[2] + 0.0;
+  whole_cdf[4] = 0.0; whole_cdf[5] = 0.0; whole_cdf[6] = 0.0 + cdf[3 * n - 1]; whole_cdf[7] = whole_cdf[6] + cdf[4 * n - 1];
+  /* ComputeMFPs, scatterers.cpp:195-220 */
+  mfp[0] = 1.0 / (whole_cdf[3] / (double)n_toa);
+  mfp[1] = 1.0 / (whole_cdf[7] / (double)n_toa);
+}

@@ -38,6 +38,11 @@ void r3d_oracle_transform(const double *in, uint32_t n, double *out);
 void r3d_oracle_rtcoef(const double *in, uint32_t n, double *out);
 void r3d_oracle_catch(double bin_dt, uint32_t n_bins, const double *in, uint32_t n, double *out);
 
+/* Scatterer::PopulateProbDists / PopulateWholeProbs / ComputeMFPs (scatterers.cpp:134-220) with ScatterParams::GSATO /
+ * XSATO / PSATO (scatparams.cpp:75-194); same outputs as r3d_build_scatterer_tables in r3d_gpu.h */
+void r3d_oracle_build_scatterer_tables(const r3d_scatter_params *par, const double *toa_theta, const double *toa_phi,
+                                       uint32_t n_toa, double *cdf, double *spol, double *whole_cdf, double *mfp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@
 //   R3D_HARNESS=randrun  same loop but with the C library generator seeded by
 //                      $R3D_HARNESS_SEED (statistical comparison runs).
 //   R3D_HARNESS=vectors  deterministic sub-kernel golden vectors.
+//   R3D_HARNESS=scatparams  the ScatterParams (nu eps a kappa el gam0) of every scatterer.
 //
 // Private members are reached with the usual "#define private public" trick,
 // applied after the standard headers are in; the reference objects themselves
@@ -403,6 +404,14 @@ int main(int argc, char * argv[]) {
       if (r3d_modelfile_write(out.c_str(), &F.d) != 0) { std::cerr << "cannot write " << out << "\n"; return 2; }
       std::cerr << "harness: wrote model (" << F.d.n_cells << " cells, " << F.d.n_scat << " scatterers, "
                 << F.d.n_toa << " TOA, " << F.d.n_seis << " seismometers) to " << out << "\n";
+      return 0;
+    }
+    if (mode == "scatparams") {            // the ScatterParams of every scatterer, in the flattener's order
+      std::ofstream f(out.c_str());
+      f.precision(17);
+      for (Scatterer * sc = Scatterer::cm_ll_first; sc != 0; sc = sc->mpllNext)
+        f << sc->mParams.nu << " " << sc->mParams.eps << " " << sc->mParams.a << " " << sc->mParams.kappa << " "
+          << sc->mParams.el << " " << sc->mParams.gam0 << "\n";
       return 0;
     }
     if (mode == "vectors") {

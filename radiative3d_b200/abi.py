@@ -84,5 +84,10 @@ EVENT_DTYPE = np.dtype([
 assert EVENT_DTYPE.itemsize == 96
 
 
+class ScatterParams(C.Structure):
+    """struct r3d_scatter_params (ScatterParams, scatparams.hpp:51-61)"""
+    _fields_ = [("nu", C.c_double), ("eps", C.c_double), ("a", C.c_double), ("kappa", C.c_double), ("el", C.c_double), ("gam0", C.c_double)]
+
+
 def as_ptr(a, ctype):
     return a.ctypes.data_as(C.POINTER(ctype))

@@ -96,6 +96,38 @@ __global__ void reduce_tally_kernel(const unsigned long long *rows, uint32_t n_r
   if (threadIdx.x == 0) counters[k] = sm[0];
 }
 
+// ScatterParams::GSATO with XSATO and PSATO inlined (scatparams.cpp:75-194); one take-off angle per thread.
+// g[0..3][n] = gpp, gps, gsp, gss; spol[n].  `numer` = 8 pi^1.5 eps^2 a^3 Gamma(kappa+1.5) / Gamma(kappa) (host).
+__global__ void gsato_kernel(r3d_scatter_params P, double numer, const double *th, const double *ph, uint32_t n, double *g, double *spol) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double psi = th[i], zeta = ph[i];
+  const double gam0 = P.gam0, gam2x = gam0 * gam0, nu = P.nu, el = P.el;
+  // XSATO (4.50)
+  const double cpsi = cos(psi), c2psi = cos(2. * psi), spsi = sin(psi), czeta = cos(zeta), szeta = sin(zeta), spsi2 = spsi * spsi;
+  const double xpp = (1. / gam2x) * (nu * (-1. + cpsi + (2. / gam2x) * spsi2) - 2. + (4. / gam2x) * spsi2);
+  const double xps = -spsi * (nu * (1. - (2. / gam0) * cpsi) - (4. / gam0) * cpsi);
+  const double xsp = (1. / gam2x) * spsi * czeta * (nu * (1. - (2. / gam0) * cpsi) - (4. / gam0) * cpsi);
+  const double xss_psi = czeta * (nu * (cpsi - c2psi) - 2. * c2psi);
+  const double xss_zeta = szeta * (nu * (cpsi - 1.) + 2. * cpsi);
+  // GSATO (4.52) with PSATO (2.10, von Karman)
+  const double pi4 = 4. * kPi, el4 = pow(el, 4.0), gam2 = pow(gam0, 2.0), a2 = P.a * P.a, ex = P.kappa + 1.5;
+  double arg = (2. * el / gam0) * sin(psi / 2.);
+  double gpp = (el4 / pi4) * (xpp * xpp) * (numer / pow(1. + a2 * arg * arg, ex));
+  if (gpp < 1.e-30) gpp = 0.;
+  arg = (el / gam0) * sqrt(1. + gam2 - 2. * gam0 * cos(psi));
+  const double pm = numer / pow(1. + a2 * arg * arg, ex);
+  double gps = (1. / gam0) * (el4 / pi4) * (xps * xps) * pm;
+  if (gps < 1.e-30) gps = 0.;
+  double gsp = gam0 * (el4 / pi4) * (xsp * xsp) * pm;
+  if (gsp < 1.e-30) gsp = 0.;
+  arg = 2. * el * sin(psi / 2.);
+  double gss = (el4 / pi4) * (xss_psi * xss_psi + xss_zeta * xss_zeta) * (numer / pow(1. + a2 * arg * arg, ex));
+  if (gss < 1.e-30) gss = 0.;
+  g[i] = gpp; g[(size_t)n + i] = gps; g[2 * (size_t)n + i] = gsp; g[3 * (size_t)n + i] = gss;
+  spol[i] = atan2(xss_zeta, xss_psi);
+}
+
 // ---------------------------------------------------------------------------
 // sub-kernel hooks (r3d_test_*)
 // ---------------------------------------------------------------------------
@@ -892,6 +924,48 @@ int rows_hook(K launch_fn, const double *in, uint32_t n, int win, int wout, doub
 }  // namespace
 
 extern "C" {
+
+int r3d_build_scatterer_tables(const r3d_scatter_params *par, uint32_t n_par, const double *toa_theta, const double *toa_phi,
+                               uint32_t n_toa, int device, double *cdf, double *spol, double *whole_cdf, double *mfp) {
+  if (!par || !toa_theta || !toa_phi || !n_toa || !cdf || !spol || !whole_cdf || !mfp) return fail(R3D_EINVAL, "null argument");
+  if (int rc = need_device()) return rc;
+  CK(cudaSetDevice(device));
+  Scratch S;
+  double *dth, *dph, *dg, *dsp;
+  const size_t n = n_toa;
+  if (int rc = S.up(toa_theta, n, &dth)) return rc;
+  if (int rc = S.up(toa_phi, n, &dph)) return rc;
+  if (int rc = S.up((const double *)nullptr, 4 * n, &dg)) return rc;
+  if (int rc = S.up((const double *)nullptr, n, &dsp)) return rc;
+  for (uint32_t p = 0; p < n_par; p++) {
+    const r3d_scatter_params &P = par[p];
+    double *c = cdf + (size_t)p * 4 * n, *w = whole_cdf + (size_t)p * 8;
+    // PSATO's numerator does not depend on the angle (scatparams.cpp:184-188)
+    const double numer = (8. * pow(kPi, 1.5) * P.eps * P.eps * P.a * P.a * P.a) * tgamma(P.kappa + 1.5) / tgamma(P.kappa);
+    gsato_kernel<<<(unsigned)((n + 255) / 256), 256>>>(P, numer, dth, dph, n_toa, dg, dsp);
+    CK(cudaGetLastError());
+    // ProbDist::Integrate (probability.cpp:21-35): the running sum in index order decides table indices, so it is formed on
+    // the host exactly as the reference forms it; each table is summed by its own thread while the next one is copied back
+    std::thread scan[4];
+    cudaError_t e = cudaSuccess;
+    for (int t = 0; t < 4 && e == cudaSuccess; t++) {
+      double *ct = c + (size_t)t * n;
+      e = cudaMemcpy(ct, dg + (size_t)t * n, n * sizeof(double), cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) scan[t] = std::thread([ct, n] { for (size_t i = 1; i < n; i++) ct[i] += ct[i - 1]; });
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(spol + (size_t)p * n, dsp, n * sizeof(double), cudaMemcpyDeviceToHost);
+    for (int t = 0; t < 4; t++) if (scan[t].joinable()) scan[t].join();
+    if (e != cudaSuccess) return fail(R3D_ECUDA, std::string("r3d_build_scatterer_tables: ") + cudaGetErrorString(e));
+    const double tot[4] = {c[n - 1], c[2 * n - 1], c[3 * n - 1], c[4 * n - 1]};
+    // PopulateWholeProbs (scatterers.cpp:170-183), integrated: IN_P = {gpp, gps, 0, 0}, IN_S = {0, 0, gsp, gss}
+    w[0] = tot[0]; w[1] = tot[0] + tot[1]; w[2] = w[1] + 0.0; w[3] = w[2] + 0.0;
+    w[4] = 0.0; w[5] = 0.0; w[6] = 0.0 + tot[2]; w[7] = w[6] + tot[3];
+    // ComputeMFPs (scatterers.cpp:195-220)
+    mfp[2 * p + 0] = 1.0 / (w[3] / (double)n_toa);
+    mfp[2 * p + 1] = 1.0 / (w[7] / (double)n_toa);
+  }
+  return 0;
+}
 
 int r3d_test_cdf_search(const double *cdf, uint32_t n_cdf, const uint32_t *k, uint32_t n, uint32_t *out, int use_guide_table) {
   if (!cdf || !k || !out || !n_cdf) return fail(R3D_EINVAL, "null argument");

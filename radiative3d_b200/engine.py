@@ -21,7 +21,7 @@ _lib = None
 
 EXPORTS = [
     "r3d_create", "r3d_run", "r3d_sync", "r3d_fetch", "r3d_reset", "r3d_device_accumulators", "r3d_stream",
-    "r3d_launch_count", "r3d_trace", "r3d_trace_events", "r3d_set_profiling", "r3d_kernel_times", "r3d_test_cdf_search", "r3d_test_path_to_boundary", "r3d_test_advance",
+    "r3d_launch_count", "r3d_trace", "r3d_trace_events", "r3d_build_scatterer_tables", "r3d_set_profiling", "r3d_kernel_times", "r3d_test_cdf_search", "r3d_test_path_to_boundary", "r3d_test_advance",
     "r3d_test_transform", "r3d_test_rtcoef", "r3d_test_catch", "r3d_destroy", "r3d_last_error", "r3d_abi_version",
 ]
 
@@ -56,6 +56,7 @@ def load_library(path=None):
     L.r3d_launch_count.argtypes = [vp, pu64]
     L.r3d_trace.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
     L.r3d_trace_events.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, vp, C.c_uint64, pu64]
+    L.r3d_build_scatterer_tables.argtypes = [C.POINTER(abi.ScatterParams), C.c_uint32, pd, pd, C.c_uint32, C.c_int, pd, pd, pd, pd]
     L.r3d_set_profiling.argtypes = [vp, C.c_int]
     L.r3d_kernel_times.argtypes = [vp, pd, pu64, pu64]
     L.r3d_test_cdf_search.argtypes = [pd, C.c_uint32, pu32, C.c_uint32, pu32, C.c_int]
@@ -232,6 +233,23 @@ def cdf_search(cdf, k, use_guide_table=1):
     _ck(L, L.r3d_test_cdf_search(_pd(cdf), cdf.size, abi.as_ptr(k, C.c_uint32), k.size, abi.as_ptr(out, C.c_uint32),
                                  use_guide_table))
     return out
+
+
+def build_scatterer_tables(params, toa_theta, toa_phi, device=0):
+    """What the reference's Scatterer constructor computes (scatterers.cpp:134-220), G values on the device.
+    params = (nu, eps, a, kappa, el, gam0) -> (cdf[4, n_toa], spol[n_toa], whole_cdf[2, 4], mfp[2]); a 2-D `params`
+    builds the tables of several scatterers in one call (leading axis = scatterer), laid out as FlatModel wants them."""
+    L = load_library()
+    th = np.ascontiguousarray(toa_theta, dtype=np.float64)
+    ph = np.ascontiguousarray(toa_phi, dtype=np.float64)
+    p2 = np.atleast_2d(np.asarray(params, dtype=np.float64))
+    n, k = th.size, p2.shape[0]
+    cdf, spol, whole, mfp = np.zeros((k, 4, n)), np.zeros((k, n)), np.zeros((k, 2, 4)), np.zeros((k, 2))
+    par = (abi.ScatterParams * k)(*[abi.ScatterParams(*map(float, row)) for row in p2])
+    _ck(L, L.r3d_build_scatterer_tables(par, k, _pd(th), _pd(ph), n, device, _pd(cdf), _pd(spol), _pd(whole), _pd(mfp)))
+    if np.ndim(params) == 1:
+        return cdf[0], spol[0], whole[0], mfp[0]
+    return cdf, spol, whole, mfp
 
 
 def transform(x):

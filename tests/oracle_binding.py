@@ -35,6 +35,8 @@ def lib():
         L.r3d_oracle_transform.argtypes = [pd, C.c_uint32, pd]
         L.r3d_oracle_rtcoef.argtypes = [pd, C.c_uint32, pd]
         L.r3d_oracle_catch.argtypes = [C.c_double, C.c_uint32, pd, C.c_uint32, pd]
+        L.r3d_oracle_build_scatterer_tables.argtypes = [C.POINTER(abi.ScatterParams), pd, pd, C.c_uint32, pd, pd, pd, pd]
+        L.r3d_oracle_build_scatterer_tables.restype = None
         for f in ("cdf_search", "path_to_boundary", "advance", "transform", "rtcoef", "catch"):
             getattr(L, "r3d_oracle_" + f).restype = None
         _LIB = L
@@ -98,6 +100,16 @@ def rtcoef(x):
 
 def catch(bin_dt, n_bins, x):
     return _rows(lib().r3d_oracle_catch, 28, 6, x, C.c_double(bin_dt), C.c_uint32(n_bins))
+
+
+def build_scatterer_tables(params, toa_theta, toa_phi):
+    th = np.ascontiguousarray(toa_theta, dtype=np.float64)
+    ph = np.ascontiguousarray(toa_phi, dtype=np.float64)
+    n = th.size
+    cdf, spol, whole, mfp = np.zeros((4, n)), np.zeros(n), np.zeros((2, 4)), np.zeros(2)
+    par = abi.ScatterParams(*[float(x) for x in params])
+    lib().r3d_oracle_build_scatterer_tables(C.byref(par), _pd(th), _pd(ph), n, _pd(cdf), _pd(spol), _pd(whole), _pd(mfp))
+    return cdf, spol, whole, mfp
 
 
 def load_bins(path):
