@@ -489,7 +489,8 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   CK(cudaDeviceGetAttribute(&prop.sharedMemPerMultiprocessor, cudaDevAttrMaxSharedMemoryPerMultiprocessor, D.device));
   CK(cudaDeviceGetAttribute(&prop.reservedSharedMemPerBlock, cudaDevAttrReservedSharedMemoryPerBlock, D.device));
   CK(cudaDeviceGetAttribute(&prop.sharedMemPerBlockOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, D.device));
-  D.threads = std::min(R3D_NT, std::max(32, env_int("R3D_THREADS", 512) / 32 * 32));
+  const int kind_threads = (d->cell_kind == R3D_CELL_CYLINDER) ? Cylinder::threads : (d->cell_kind == R3D_CELL_SHELL) ? Shell::threads : Tetra::threads;
+  D.threads = std::min(kind_threads, std::max(32, env_int("R3D_THREADS", kind_threads) / 32 * 32));
   D.blocks_per_sm = std::max(1, env_int("R3D_BLOCKS_PER_SM", 1));
   cudaFuncAttributes fattr;
   CK(cudaFuncGetAttributes(&fattr, pick_propagate(d->cell_kind, true, true)));
@@ -505,7 +506,7 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   const size_t for_slots = D.smem_block - D.table_bytes;
   D.max_slots[0] = (uint32_t)std::min<size_t>(for_slots / R3D_SLOT_BYTES / 32 * 32, 65504);
   D.max_slots[1] = (uint32_t)std::min<size_t>(for_slots / R3D_SLOT_BYTES_TRACE / 32 * 32, 65504);
-  if (int cap = env_int("R3D_SLOTS_PER_BLOCK", 1280)) {
+  if (int cap = env_int("R3D_SLOTS_PER_BLOCK", 0)) {
     for (int t = 0; t < 2; t++) D.max_slots[t] = std::max(32u, std::min(D.max_slots[t], (uint32_t)cap / 32 * 32));
   }
   if (D.max_slots[1] < 32) return fail(R3D_EUNSUPPORTED, "shared memory too small for the phonon slots");

@@ -28,12 +28,7 @@
 namespace r3d {
 
 #define R3D_FULL 0xffffffffu
-#ifndef R3D_NT
-#define R3D_NT 512             // upper bound of threads per CTA (the launch may use fewer)
-#endif
-#ifndef R3D_MINBLOCKS
-#define R3D_MINBLOCKS 1        // 512 x 1 => 128 registers per thread; 256 threads x 2 CTAs per SM uses the same budget
-#endif
+#define R3D_NT 512             // most threads per CTA of any cell kind (Cell::threads sets each kernel's launch bound, one CTA per SM)
 
 struct Job {
   unsigned long long first, n, seed;
@@ -741,7 +736,7 @@ R3D_DEV void bend_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, co
 // the kernel: persistent CTAs, S slots each
 // =====================================================================================================
 template <class Cell, bool TRACE, bool SMALL>
-__global__ void __launch_bounds__(R3D_NT, R3D_MINBLOCKS)
+__global__ void __launch_bounds__(Cell::threads, 1)
 propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes, unsigned long long *block_tally,
                  unsigned long long *block_clock) {
   __shared__ unsigned long long tally_sm[R3D_NT / 32][R3D_NCOUNTERS];
