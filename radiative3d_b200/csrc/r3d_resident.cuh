@@ -502,6 +502,12 @@ R3D_DEV void refill_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
 // works on U draws at once and issues each stage's loads for all of them before it consumes any, so a warp has
 // 32 U chains in flight instead of 32 (ncu: with one draw per thread phase 2 took two thirds of the kernel, waiting).
 // =====================================================================================================
+#ifndef R3D_FINAL
+#define R3D_FINAL 8u         // a guide span of up to this many CDF entries is read in one round trip; wider ones are narrowed
+#endif                       // first (ncu: with 4, the narrowing loop ran at 4.4 of 32 lanes and cost 6 % of all instructions)
+#ifndef R3D_CHUNK_CLOCKS
+#define R3D_CHUNK_CLOCKS 0   // 1: every warp clocks its chunks by kind (make clocks; scripts/chunk_clocks.py); 3.7 % of all instructions
+#endif
 #ifndef R3D_DRAW_U
 #define R3D_DRAW_U 1
 #endif
@@ -539,7 +545,7 @@ R3D_DEV void draw_batch(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
     for (;;) {
       bool wide = false;
 #pragma unroll
-      for (int u = 0; u < U; u++) wide |= (k2[u] - k1[u] > 4);
+      for (int u = 0; u < U; u++) wide |= (k2[u] - k1[u] > R3D_FINAL);
       if (!__any_sync(R3D_FULL, wide)) break;
       double pv[U][7];
 #pragma unroll
@@ -547,12 +553,12 @@ R3D_DEV void draw_batch(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
         const uint32_t span = k2[u] - k1[u];
 #pragma unroll
         for (uint32_t i = 0; i < 7; i++)
-          pv[u][i] = (span > 4) ? ld_table(cdf[u] + k1[u] + (uint32_t)(((unsigned long long)span * (i + 1)) >> 3)) : 0.0;
+          pv[u][i] = (span > R3D_FINAL) ? ld_table(cdf[u] + k1[u] + (uint32_t)(((unsigned long long)span * (i + 1)) >> 3)) : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const uint32_t span = k2[u] - k1[u];
-        if (span > 4) {
+        if (span > R3D_FINAL) {
           uint32_t c = 0;
 #pragma unroll
           for (uint32_t i = 0; i < 7; i++) c += (r[u] <= pv[u][i]) ? 0u : 1u;
@@ -568,16 +574,16 @@ R3D_DEV void draw_batch(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
         }
       }
     }
-    double v[U][4];
+    double v[U][R3D_FINAL];
 #pragma unroll
     for (int u = 0; u < U; u++)
 #pragma unroll
-      for (uint32_t i = 0; i < 4; i++) v[u][i] = (k1[u] + i < k2[u]) ? ld_table(cdf[u] + k1[u] + i) : pinf();
+      for (uint32_t i = 0; i < R3D_FINAL; i++) v[u][i] = (k1[u] + i < k2[u]) ? ld_table(cdf[u] + k1[u] + i) : pinf();
 #pragma unroll
     for (int u = 0; u < U; u++) {
       uint32_t c = 0;
 #pragma unroll
-      for (uint32_t i = 0; i < 4; i++) c += (r[u] <= v[u][i]) ? 0u : 1u;
+      for (uint32_t i = 0; i < R3D_FINAL; i++) c += (r[u] <= v[u][i]) ? 0u : 1u;
       ti[u] = k1[u] + c;
     }
   } else {
@@ -792,7 +798,9 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
         if (c >= cA + cR) break;
         int out = OUT_NONE;
         uint32_t s = 0;
+#if R3D_CHUNK_CLOCKS
         const long long tc = clock64();
+#endif
         if (c < cA) {
           const uint32_t j = c * 32u + lane;
           if (j < nA) { s = q[j]; out = advance_one<Cell, TRACE>(M, J, A, tab, s, T); }
@@ -801,7 +809,9 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
           if (j < nR) { s = q[S - 1u - j]; refill_one<TRACE>(M, J, A, s, base + j, T); out = OUT_SRC; }
         }
         route<TRACE>(A, C, nxt, out, s);
+#if R3D_CHUNK_CLOCKS
         if (lane == 0) { const int kd = (c < cA) ? 0 : 1; atomicAdd(&C.t_kind[kd], (unsigned long long)(clock64() - tc)); atomicAdd(&C.n_kind[kd], 1u); }
+#endif
       }
     }
     __syncthreads();
@@ -818,7 +828,9 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
       for (;;) {
         const uint32_t c = next_chunk(&C.cursor[1]);
         if (c >= c4) break;
+#if R3D_CHUNK_CLOCKS
         const long long tc = clock64();
+#endif
         if (c >= c3) {
           const uint32_t j = (c - c3) * 32u + lane;
           int out = OUT_NONE;
@@ -840,7 +852,9 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
 #pragma unroll
           for (int u = 0; u < R3D_DRAW_U; u++) route<TRACE>(A, C, nxt, have[u] ? OUT_ADV : OUT_NONE, s[u]);
         }
+#if R3D_CHUNK_CLOCKS
         if (lane == 0) { const int kd = (c < c1 || c >= c3) ? 2 : 3; atomicAdd(&C.t_kind[kd], (unsigned long long)(clock64() - tc)); atomicAdd(&C.n_kind[kd], 1u); }
+#endif
       }
     }
     __syncthreads();

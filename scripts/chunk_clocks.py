@@ -2,6 +2,7 @@
 """Scratch: warp-time by kind of chunk (R3D_TIMING=1 makes r3d_kernel_times print it).  usage: chunk_clocks.py <config> <deg> <n>"""
 import os, sys
 os.environ["R3D_TIMING"] = "1"
+os.environ.setdefault("R3D_LIBRARY", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "radiative3d_b200", "libr3dgpu_clocks.so"))   # make -C radiative3d_b200/csrc clocks
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from radiative3d_b200 import abi, engine, reference_host
