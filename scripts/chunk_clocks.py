@@ -2,7 +2,11 @@
 """Scratch: warp-time by kind of chunk (R3D_TIMING=1 makes r3d_kernel_times print it).  usage: chunk_clocks.py <config> <deg> <n>"""
 import os, sys
 os.environ["R3D_TIMING"] = "1"
-os.environ.setdefault("R3D_LIBRARY", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "radiative3d_b200", "libr3dgpu_clocks.so"))   # make -C radiative3d_b200/csrc clocks
+_clk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "radiative3d_b200", "libr3dgpu_clocks.so")   # make -C radiative3d_b200/csrc clocks
+if os.path.exists(_clk):
+    os.environ.setdefault("R3D_LIBRARY", _clk)
+else:
+    print("chunk_clocks.py: libr3dgpu_clocks.so not built (make -C radiative3d_b200/csrc clocks): per-chunk figures will be zero", file=sys.stderr)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from radiative3d_b200 import abi, engine, reference_host
