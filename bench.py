@@ -182,6 +182,9 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
     args.warmup = max(args.warmup, 3)
+    # stdout carries ONE JSON line: whatever libraries print to fd 1 meanwhile (NCCL's version banner) goes to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import numpy as np
     import torch
@@ -346,7 +349,8 @@ def main():
         }
         if cpu:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
