@@ -9,19 +9,23 @@
 //     the draw and interface kernels touch a sparse subset of the struct-of-arrays pool, so every 8-byte field
 //     costs a 32-byte sector: 400 B of DRAM traffic per draw and 1.1 kB per face event, 50-67 % of DRAM
 //     bandwidth spent on state that is never reused by another SM (profiles/r1_wavefront_hbm.md).
-// Here every CTA is persistent and owns S phonon slots in its shared memory (144 B per slot, ~1500 slots in the
-// 227 KB of a B200 SM).  The CTA alternates two phases, separated by __syncthreads():
+// Here every CTA is persistent (one per SM) and owns S phonon slots in its shared memory: 146 B per slot, 1376 slots in a
+// 196 KB carve-out, which leaves 60 KB of the SM's 256 KB to L1.  The CTA alternates two phases, separated by
+// __syncthreads():
 //   phase 1  advance  (slots ready to move)  time-out / validity checks, distance to boundary, path-length draw,
-//                                            move, cheap hand-overs inline; classification of the event
-//            refill   (free slots)           new phonon indices from the global work counter; source ray type
-//   phase 2  draw     (queued table draws)   exact guide-table CDF search + take-off-angle fetch from HBM/L2, then
+//                                            move, cheap hand-overs inline; classification of the event; all draws the
+//                                            event will consume are taken from its Philox block here, in order
+//            refill   (free slots)           new phonon indices from the job's work counter; source ray type
+//   phase 2  face     (queued face events)   seismometer catch through the uniform-grid index, R/T coefficients
+//            draw     (queued table draws)   exact guide-table CDF search + take-off-angle fetch from HBM/L2, then
 //                                            the new phonon's direction or Phonon::Transform
-//            face     (queued face events)   seismometer catch through the uniform-grid index, R/T coefficients,
-//                                            ray bending
+//            bend     (queued plain bends)   Snell bending at faces that neither collect nor reflect
 // Within a phase, warps pull 32-entry chunks of ONE kind of work from index queues in shared memory, so a warp
 // executes one kind of event (P and S face events are queued apart, source and scatter draws too).  State never
-// leaves the SM; HBM sees only the table gathers (~150 B per draw) and the bin atomics.  Several CTAs per SM
-// (R3D_BLOCKS_PER_SM) run in different phases and fill each other's barrier bubbles.
+// leaves the SM; HBM sees only the table gathers (~150 B per draw) and the bin atomics.
+// The phases are also what keeps the working set of CODE small: the same slots behind barrier-free ring queues, with
+// every kind of event running at once, thrashed the instruction caches (9 cycles of fetch stall per issued instruction)
+// and ran 35 % slower (profiles/r1_resident_kernel.md, which also records the other variants that were measured).
 #pragma once
 #include "r3d_device.cuh"
 
