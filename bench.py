@@ -337,7 +337,7 @@ def main():
                                    f"TOA degree {TOA_DEGREE} ({model.n_toa} take-off angles, {h2d / 1e9:.2f} GB of tables)",
                        "phonons_per_gpu_per_step": per, "global_phonons_per_step": per * world, "parallelism": f"phonon-index sharding x{world}, "
                        "one NCCL all-reduce of the bins at the end",
-                       "cache": "inputs larger than L2: 0.42 GB of CDF tables + 0.06 GB of guide tables, gathered at random, vs 126 MB L2",
+                       "cache": "inputs larger than L2: 0.42 GB of CDF tables + 0.23 GB of guide tables, gathered at random, vs 126 MB L2",
                        "timing": "CUDA events on the launching stream (r3d_sync) + torch events around the all-reduce, max over ranks",
                        "wall_ms_per_step": 1e3 * wall_s / K,
                        "loop_events_per_second": events_total / dev_s, "events_per_phonon": events_total / total,

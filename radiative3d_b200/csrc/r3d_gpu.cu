@@ -448,9 +448,9 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   CK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, D.stream));
   CK(cudaStreamSynchronize(D.stream));
   int bits = env_int("R3D_GUIDE_BITS", -1);
-  if (bits < 0) {                         // default: about 4 table entries per bucket
-    bits = 0;
-    while ((1ull << (bits + 2)) < nt && bits < 24) bits++;
+  if (bits < 0) {                         // default: about one table entry per bucket (TOA degree 9: 2^23 buckets, 32 MB per table).
+    bits = 0;                             // With 4 per bucket 62-97 % of the warps of the bench workload had a lane whose bucket was
+    while ((1ull << bits) < nt && bits < 24) bits++;      // wider than the final read and took the narrowing round trip; now 10-45 %
   }
   if (bits > 24) bits = 24;
   if (hbad || bits == 0 || nt < 16) {
