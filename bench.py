@@ -47,132 +47,82 @@ def algorithmic_bytes_per_draw(n_toa):
 
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock, throttle reasons and power sampled every 10 ms through NVML while the timed region runs (nvidia-smi every
+    200 ms when the NVML binding is missing)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self.halt, self.how = [], None, None, False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip()]
+            phys = int(ids[index]) if ids and all(v.strip().isdigit() for v in ids) and index < len(ids) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.how = pynvml, "nvml every 10 ms"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi every 200 ms"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        bits = [(getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8), 0), (getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), 1),
+                (getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), 2), (getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4), 3)]
+        reasons_of = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.halt:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(reasons_of(self.handle))
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                row = [str(sm), str(self.max_sm)] + ["Not Active"] * 4 + [str(pw)]
+                for b, k in bits:
+                    if mask & b:
+                        row[2 + k] = "Active"
+                self.rows.append((time.perf_counter(), row))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
+        if not self.proc and not self.nvml:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["neither NVML nor nvidia-smi available"]}
+        if self.nvml:
+            self.halt = True
+            self.thread.join(timeout=1.0)
+        else:
+            time.sleep(0.25)
+            self.proc.terminate()
         rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
         sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows for n, v in zip(self.NAMES, r[2:6]) if v.lower().startswith("active")})
         pw = [float(r[6]) for r in rows if len(r) > 6 and r[6].replace(".", "").isdigit()]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(rows), "power_w_max": max(pw) if pw else None}
+                "reasons": reasons, "samples": len(rows), "power_w_max": max(pw) if pw else None, "how": self.how}
 
 
-def run_reference_binary(n_phonons, outdir):
-    """One run of the UNMODIFIED reference program on this workload; returns wall seconds."""
-    from radiative3d_b200 import workloads
-    os.makedirs(outdir, exist_ok=True)
-    t = time.perf_counter()
-    p = subprocess.run([REF_MAIN] + workloads.cmdline(WORKLOAD, n_phonons, TOA_DEGREE, outdir), cwd=outdir,
-                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    if p.returncode != 0:
-        raise RuntimeError(f"reference binary failed with rc {p.returncode}")
-    return time.perf_counter() - t
-
-
-def cpu_baseline_one_core(sample=1_500_000):
-    """The reference binary on ONE host core: (sample phonons) / (wall - model-build time)."""
-    if not os.path.exists(REF_MAIN):
-        return cpu_baseline_port(sample // 10, 1)
-    with tempfile.TemporaryDirectory() as tmp:
-        t_init = run_reference_binary(10, os.path.join(tmp, "init"))
-        t_run = run_reference_binary(sample, os.path.join(tmp, "run"))
-    return {"value": sample / max(t_run - t_init, 1e-9), "unit": "phonons/s", "cores": 1, "kind": "reference",
-            "sample": f"{sample} phonons of {WORKLOAD} at TOA degree {TOA_DEGREE} through oracle/_ref/r3d_ref_main "
-                      f"(unmodified reference, -O3), {t_run:.1f} s wall minus {t_init:.1f} s model build (N=10 run)"}
-
-
-def cpu_baseline_port(sample, threads):
-    """Fallback when the reference binary did not travel: the C oracle (a port), on `threads` host threads."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_binding as ob
-    from radiative3d_b200 import reference_host
-    m = reference_host.build_model(WORKLOAD, TOA_DEGREE)
-    ob.run(m, 0, 1000, SEED, nthreads=threads)
-    t = time.perf_counter()
-    ob.run(m, 0, sample, SEED, nthreads=threads)
-    dt = time.perf_counter() - t
-    return {"value": sample / dt, "unit": "phonons/s", "cores": threads, "kind": "port",
-            "sample": f"{sample} phonons of {WORKLOAD} at TOA degree {TOA_DEGREE} through oracle/liboracle.so"}
-
-
-# ---------------------------------------------------------------------------------------------------------------
-def reference_arm(args):
-    """bench.py --impl reference: the reference's CPU implementation on all host cores (independent processes)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
-    cores = max(1, min(os.cpu_count() or 1, 32))
-    per_proc = 400_000
-    base = {"metric": "phonons traced/sec", "unit": "phonons/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "impl": "reference", "gpu_launches": 0,
-            "config": {"workload": f"{WORKLOAD} (do-halfspace-nearsrc50.sh), TOA degree {TOA_DEGREE}",
-                       "phonons_per_step": cores * per_proc, "note": "bounded sample of the GPU arm's batch"}}
-    if not os.path.exists(REF_MAIN):
-        cb = cpu_baseline_port(cores * 20000, cores)
-        base.update(value=cb["value"], ms_per_step=None, cpu_baseline=cb,
-                    e2e={"value": cb["value"], "unit": "phonons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
-        print(json.dumps(base))
-        return 0
-    from radiative3d_b200 import workloads
-    with tempfile.TemporaryDirectory() as tmp:
-        t_init = run_reference_binary(10, os.path.join(tmp, "init"))
-
-        def step(i):       # (the reference seeds with time(NULL): equal seeds duplicate phonons, not cost)
-            t = time.perf_counter()
-            ps = []
-            for c in range(cores):
-                d = os.path.join(tmp, f"s{i}_{c}")
-                os.makedirs(d, exist_ok=True)
-                ps.append(subprocess.Popen([REF_MAIN] + workloads.cmdline(WORKLOAD, per_proc, TOA_DEGREE, d), cwd=d,
-                                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
-            for p in ps:
-                if p.wait() != 0:
-                    raise RuntimeError("reference binary failed")
-            return time.perf_counter() - t
-
-        for i in range(min(args.warmup, 1)):          # one warm-up pass is enough for a CPU process farm
-            step(-1 - i)
-        times = [step(i) for i in range(args.steps)]
-    sim = [max(t - t_init, 1e-9) for t in times]
-    value = cores * per_proc * len(sim) / sum(sim)
-    cb = {"value": value, "unit": "phonons/s", "cores": cores, "kind": "reference",
-          "sample": f"{cores} independent processes x {per_proc} phonons per step through oracle/_ref/r3d_ref_main; "
-                    f"wall of the slowest minus {t_init:.1f} s model build"}
-    base.update(value=value, ms_per_step=1e3 * sum(sim) / len(sim), cpu_baseline=cb,
-                e2e={"value": value, "unit": "phonons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
-    print(json.dumps(base))
-    return 0
-
-
-# ---------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--per-gpu", type=int, default=PER_GPU, help="phonons per GPU per step")
