@@ -119,6 +119,95 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(rows), "power_w_max": max(pw) if pw else None, "how": self.how}
 
 
+def run_reference_binary(n_phonons, outdir):
+    """One run of the UNMODIFIED reference program on this workload; returns wall seconds."""
+    from radiative3d_b200 import workloads
+    os.makedirs(outdir, exist_ok=True)
+    t = time.perf_counter()
+    p = subprocess.run([REF_MAIN] + workloads.cmdline(WORKLOAD, n_phonons, TOA_DEGREE, outdir), cwd=outdir,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    if p.returncode != 0:
+        raise RuntimeError(f"reference binary failed with rc {p.returncode}")
+    return time.perf_counter() - t
+
+
+def cpu_baseline_one_core(sample=1_500_000):
+    """The reference binary on ONE host core: (sample phonons) / (wall - model-build time)."""
+    if not os.path.exists(REF_MAIN):
+        return cpu_baseline_port(sample // 10, 1)
+    with tempfile.TemporaryDirectory() as tmp:
+        t_init = run_reference_binary(10, os.path.join(tmp, "init"))
+        t_run = run_reference_binary(sample, os.path.join(tmp, "run"))
+    return {"value": sample / max(t_run - t_init, 1e-9), "unit": "phonons/s", "cores": 1, "kind": "reference",
+            "sample": f"{sample} phonons of {WORKLOAD} at TOA degree {TOA_DEGREE} through oracle/_ref/r3d_ref_main "
+                      f"(unmodified reference, -O3), {t_run:.1f} s wall minus {t_init:.1f} s model build (N=10 run)"}
+
+
+def cpu_baseline_port(sample, threads):
+    """Fallback when the reference binary did not travel: the C oracle (a port), on `threads` host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    from radiative3d_b200 import reference_host
+    m = reference_host.build_model(WORKLOAD, TOA_DEGREE)
+    ob.run(m, 0, 1000, SEED, nthreads=threads)
+    t = time.perf_counter()
+    ob.run(m, 0, sample, SEED, nthreads=threads)
+    dt = time.perf_counter() - t
+    return {"value": sample / dt, "unit": "phonons/s", "cores": threads, "kind": "port",
+            "sample": f"{sample} phonons of {WORKLOAD} at TOA degree {TOA_DEGREE} through oracle/liboracle.so"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def reference_arm(args):
+    """bench.py --impl reference: the reference's CPU implementation on all host cores (independent processes)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    per_proc = 400_000
+    base = {"metric": "phonons traced/sec", "unit": "phonons/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "impl": "reference", "gpu_launches": 0,
+            "config": {"workload": f"{WORKLOAD} (do-halfspace-nearsrc50.sh), TOA degree {TOA_DEGREE}",
+                       "phonons_per_step": cores * per_proc, "note": "bounded sample of the GPU arm's batch"}}
+    if not os.path.exists(REF_MAIN):
+        cb = cpu_baseline_port(cores * 20000, cores)
+        base.update(value=cb["value"], ms_per_step=None, cpu_baseline=cb,
+                    e2e={"value": cb["value"], "unit": "phonons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(base))
+        return 0
+    from radiative3d_b200 import workloads
+    with tempfile.TemporaryDirectory() as tmp:
+        t_init = run_reference_binary(10, os.path.join(tmp, "init"))
+
+        def step(i):       # (the reference seeds with time(NULL): equal seeds duplicate phonons, not cost)
+            t = time.perf_counter()
+            ps = []
+            for c in range(cores):
+                d = os.path.join(tmp, f"s{i}_{c}")
+                os.makedirs(d, exist_ok=True)
+                ps.append(subprocess.Popen([REF_MAIN] + workloads.cmdline(WORKLOAD, per_proc, TOA_DEGREE, d), cwd=d,
+                                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+            for p in ps:
+                if p.wait() != 0:
+                    raise RuntimeError("reference binary failed")
+            return time.perf_counter() - t
+
+        for i in range(min(args.warmup, 1)):          # one warm-up pass is enough for a CPU process farm
+            step(-1 - i)
+        times = [step(i) for i in range(args.steps)]
+    sim = [max(t - t_init, 1e-9) for t in times]
+    value = cores * per_proc * len(sim) / sum(sim)
+    cb = {"value": value, "unit": "phonons/s", "cores": cores, "kind": "reference",
+          "sample": f"{cores} independent processes x {per_proc} phonons per step through oracle/_ref/r3d_ref_main; "
+                    f"wall of the slowest minus {t_init:.1f} s model build"}
+    base.update(value=value, ms_per_step=1e3 * sum(sim) / len(sim), cpu_baseline=cb,
+                e2e={"value": value, "unit": "phonons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    print(json.dumps(base))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
