@@ -701,8 +701,10 @@ int r3d_fetch(r3d_handle *h, double *energies, uint64_t *counts, uint64_t *count
   std::vector<double> e;
   std::vector<unsigned long long> c;
   unsigned long long k[R3D_NCOUNTERS], ksum[R3D_NCOUNTERS] = {0};
-  if (energies) memset(energies, 0, nb * R3D_BIN_NF64 * sizeof(double));
-  if (counts) memset(counts, 0, nb * R3D_BIN_NCNT * sizeof(uint64_t));
+  if (h->devs.empty()) {                       // (the first device's copy below overwrites; nothing to clear otherwise)
+    if (energies) memset(energies, 0, nb * R3D_BIN_NF64 * sizeof(double));
+    if (counts) memset(counts, 0, nb * R3D_BIN_NCNT * sizeof(uint64_t));
+  }
   for (size_t g = 0; g < h->devs.size(); g++) {
     DevState &D = *h->devs[g];
     if (int rc = drain(D)) return rc;

@@ -135,11 +135,19 @@ class Engine:
         _ck(self._L, self._L.r3d_sync(self._h, C.byref(t)))
         return t.value
 
-    def fetch(self):
-        """(energies[n_seis,n_bins,5], counts[n_seis,n_bins,2], counters[8]) summed over devices."""
+    def fetch(self, out=None):
+        """(energies[n_seis,n_bins,5], counts[n_seis,n_bins,2], counters[8]) summed over devices.  `out` = (energies, counts)
+        host arrays of those shapes to fill instead of new ones (C-contiguous float64 / uint64; pinned memory makes the
+        device-to-host copy direct)."""
         m = self.model
-        e = np.zeros((m.n_seis, m.n_bins, abi.R3D_BIN_NF64))
-        c = np.zeros((m.n_seis, m.n_bins, abi.R3D_BIN_NCNT), dtype=np.uint64)
+        if out is not None:
+            e, c = out
+            if (e.shape != (m.n_seis, m.n_bins, abi.R3D_BIN_NF64) or e.dtype != np.float64 or not e.flags.c_contiguous or
+                    c.shape != (m.n_seis, m.n_bins, abi.R3D_BIN_NCNT) or c.dtype != np.uint64 or not c.flags.c_contiguous):
+                raise ValueError("fetch(out=...): need C-contiguous float64 [n_seis,n_bins,5] and uint64 [n_seis,n_bins,2] arrays")
+        else:
+            e = np.zeros((m.n_seis, m.n_bins, abi.R3D_BIN_NF64))
+            c = np.zeros((m.n_seis, m.n_bins, abi.R3D_BIN_NCNT), dtype=np.uint64)
         k = np.zeros(abi.R3D_NCOUNTERS, dtype=np.uint64)
         diag = C.c_uint32()
         _ck(self._L, self._L.r3d_fetch(self._h, _pd(e), abi.as_ptr(c, C.c_uint64), abi.as_ptr(k, C.c_uint64), C.byref(diag)))

@@ -169,3 +169,21 @@ def test_two_devices_in_one_handle():
         e2, c2, k2 = eng.fetch()
     assert np.array_equal(c1, c2) and np.array_equal(k1[:7], k2[:7])
     assert bin_energy_err(e1, e2) <= 1e-12
+
+
+def test_fetch_into_caller_buffers():
+    """r3d_fetch fills the arrays it is given (every element, so stale contents cannot survive) and rejects wrong shapes."""
+    m, z = load_golden("halfspace")
+    with engine.Engine(m) as eng:
+        eng.run_simulation(20000, seed=5)
+        eng.sync()
+        e, c, k = eng.fetch()
+        e2 = np.full(e.shape, 7.0)
+        c2 = np.full(c.shape, 9, dtype=np.uint64)
+        e3, c3, k3 = eng.fetch(out=(e2, c2))
+        assert e3 is e2 and c3 is c2
+        assert np.array_equal(e2, e) and np.array_equal(c2, c) and np.array_equal(k3, k)
+        with pytest.raises(ValueError):
+            eng.fetch(out=(e2[:, :-1], c2))
+        with pytest.raises(ValueError):
+            eng.fetch(out=(e2.astype(np.float32), c2))
