@@ -428,7 +428,26 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   lap("cdf tables, spol");
   if (int rc = dev_upload(D, &M.cell_params, d->cell_params, nc * d->cell_nparam)) return rc;
   if (int rc = dev_upload(D, &M.cell_scat, d->cell_scat, nc)) return rc;
-  if (int rc = dev_upload(D, &M.face_flags, d->face_flags, nc * nf)) return rc;
+  {
+    // Layered (cylinder) cells have one velocity per wave type, so whether a neighbour face bends the ray or hands it
+    // over unchanged (CellFace::VelocityJump > 1e-5, phonons.cpp:225-255, media_cellface.cpp:83-99) is a property of the
+    // face: evaluated once here with the reference's own expression (plain IEEE double operations, no contraction
+    // possible) and kept in two library-private bits of the flag byte, instead of two divisions per face crossing.
+    std::vector<uint8_t> fl(d->face_flags, d->face_flags + nc * nf);
+    if (d->cell_kind == R3D_CELL_CYLINDER) {
+      const size_t np = d->cell_nparam;
+      for (size_t i = 0; i < nc; i++) for (size_t f = 0; f < nf; f++) {
+        uint8_t &x = fl[i * nf + f];
+        x &= 0x0f;
+        if (!(x & R3D_FACE_ADJOIN)) continue;
+        const double *c = d->cell_params + i * np, *o = d->cell_params + (size_t)d->face_other_cell[i * nf + f] * np;
+        volatile double dvp = std::fabs(2 * (o[0] - c[0]) / (o[0] + c[0])), dvs = std::fabs(2 * (o[1] - c[1]) / (o[1] + c[1]));
+        const double jump = (dvp > dvs) ? dvp : dvs;
+        x |= R3D_FACE_JUMP_KNOWN | ((jump > 0.00001) ? R3D_FACE_JUMP : 0);
+      }
+    }
+    if (int rc = dev_upload(D, &M.face_flags, fl.data(), nc * nf)) return rc;
+  }
   if (int rc = dev_upload(D, &M.face_other, d->face_other_cell, nc * nf)) return rc;
   if (int rc = dev_upload(D, &M.seis, d->seis, (size_t)d->n_seis * R3D_SEIS_NPARAM)) return rc;
   double4 *sph = nullptr;

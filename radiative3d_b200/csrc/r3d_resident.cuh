@@ -261,6 +261,7 @@ R3D_DEV int face_action(const DevModel &M, const TabT &tab, uint32_t fl, uint32_
   if (fl & R3D_FACE_REFLECT) return FACE_FULLRT;                                    // phonons.cpp:640-646
   if (fl & R3D_FACE_ADJOIN) {                                                       // Phonon::Refract, phonons.cpp:225-255
     if (fl & R3D_FACE_DISCON) return FACE_FULLRT;
+    if (fl & R3D_FACE_JUMP_KNOWN) return (fl & R3D_FACE_JUMP) ? FACE_BEND : FACE_CONTINUOUS;     // layered cells: decided in r3d_create
     return (velocity_jump<Cell>(M, tab, cell, other, loc) > 0.00001) ? FACE_BEND : FACE_CONTINUOUS;
   }
   return FACE_LOST;                                                                 // phonons.cpp:675
