@@ -108,7 +108,7 @@ struct Slots {
   // trace mode only: [4][S] catches, scatters, iterations, event reports made
   R3D_DEV uint32_t &tr(int which, uint32_t s) const { return reinterpret_cast<uint32_t *>(r3d_smem + (size_t)S * 136 + table_bytes)[(uint32_t)which * S + s]; }
   // queues of slot indices: buffer 0 / 1 = [cur|next] ready-to-advance slots from the front, free slots from the back;
-  // buffer 2 = table draws: scatter draws from the front, source draws from the back; buffer 3 = face events: P from
+  // buffer 2 = table draws: scatter draws from the front, slots freed in phase 1 (waiting for a new phonon) from the back; buffer 3 = face events: P from
   // the front, S from the back; buffer 4 = plain ray bending at a face (no catch, no R/T solve)
   R3D_DEV uint16_t *queue(uint32_t buf) const {
     return reinterpret_cast<uint16_t *>(r3d_smem + (size_t)S * (TRACE ? 152 : 136) + table_bytes) + (size_t)buf * S;
@@ -125,7 +125,7 @@ struct Ctl {
   unsigned long long t_kind[4], t_idle;
   uint32_t n_kind[4];
   unsigned long long base;          // first phonon (relative to the job) granted to this CTA in this iteration
-  uint32_t granted, exhausted, done, cursor[2];
+  uint32_t grant_a, grant_b, exhausted, done, cursor[2];       // grant_a, grant_b: new phonons for the two lists of free slots
   uint32_t cnt[9];
   unsigned long long t_phase[2];    // clock cycles spent in phase 1 / phase 2 (thread 0's view)
   uint32_t iterations;
@@ -480,7 +480,7 @@ R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
   return out;
 }
 
-// phase 1b: a free slot takes the next phonon: ShearDislocation::GenerateEventPhonon (events.cpp:111-124) ->
+// phase 2 (first half of a new-phonon chunk): a free slot takes the next phonon: ShearDislocation::GenerateEventPhonon (events.cpp:111-124) ->
 // PhononSource::GenerateRandomPhonon (sources.cpp:156-170) -> Phonon ctor (phonons.hpp:193-207)
 template <bool TRACE>
 R3D_DEV void refill_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, uint32_t s, unsigned long long rel, Tally &T) {
@@ -488,8 +488,7 @@ R3D_DEV void refill_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
   Rng g; g.init(J.seed, idx);
   g.block(0);
   const uint32_t rt3 = cdf_search_small(M.src_whole, 3, g.w[0] >> 1);
-  A.req(s) = make_uint2(g.w[1] >> 1, rt3);                    // the take-off angle is drawn in phase 2
-  prefetch_guide(M, true, rt3, g.w[1] >> 1);
+  A.req(s) = make_uint2(g.w[1] >> 1, rt3);                    // the take-off angle is drawn next, in the same chunk
   A.tp(s) = make_double2(0.0, 0.0);
   A.ra(s) = make_double2(0.0, 0.0);
   A.lxy(s) = make_double2(M.src_loc[0], M.src_loc[1]);
@@ -760,7 +759,7 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
 #pragma unroll
     for (int k = 0; k < 9; k++) C.cnt[k] = 0;
     C.cnt[OUT_FREE] = S;
-    C.exhausted = 0; C.done = 0; C.t_phase[0] = 0; C.t_phase[1] = 0; C.iterations = 0;
+    C.exhausted = 0; C.done = 0; C.grant_a = 0; C.grant_b = 0; C.t_phase[0] = 0; C.t_phase[1] = 0; C.iterations = 0;
     for (int k = 0; k < 4; k++) { C.t_kind[k] = 0; C.n_kind[k] = 0; }
     C.t_idle = 0;
   }
@@ -771,65 +770,74 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
   const long long t_begin = clock64();
   __syncthreads();
 
+  // A slot whose phonon dies in phase 1 gets its next phonon in phase 2 of the SAME iteration (grant at the phase boundary,
+  // then ray type + take-off angle in one chunk), so that it advances again in the next phase 1.  (With the refill in the
+  // next phase 1 and the source draw in the phase 2 after it, every phonon cost its slot one iteration in which nothing
+  // advanced: 4.4 iterations for the 3.4 events of a phonon of the halfspace workload.)  Two lists of free slots: (B) the
+  // slots freed in phase 1, at the back of the draw queue (buffer 2) - they cannot stay in the next advance queue's buffer,
+  // which they re-enter from the front in phase 2 while their old entries still occupy its back; (A) the slots freed in
+  // phase 2 (phonons lost at a collecting face: rare) and, at the start, all slots: the back of the current advance queue.
   for (;;) {
     const int nxt = cur ^ 1;
+    if (threadIdx.x == 0) {
+      C.cnt[nxt * 2 + OUT_ADV] = 0; C.cnt[nxt * 2 + OUT_FREE] = 0;
+      C.cnt[CNT_SCAT] = 0; C.cnt[CNT_SRC] = 0; C.cnt[CNT_FP] = 0; C.cnt[CNT_FS] = 0; C.cnt[CNT_BEND] = 0;
+      C.cursor[0] = 0; C.cursor[1] = 0;
+      C.done = (C.cnt[cur * 2 + OUT_ADV] == 0 && C.exhausted);
+      t0 = clock64();
+    }
+    __syncthreads();
+    if (C.done) break;
+
+    // ---- phase 1: advance chunks ---------------------------------------------------------------------------------
+    {
+      const uint32_t nA = C.cnt[cur * 2 + OUT_ADV];
+      const uint32_t cA = (nA + 31u) >> 5;
+      const uint16_t *q = A.queue((uint32_t)cur);
+      for (;;) {
+        const uint32_t c = next_chunk(&C.cursor[0]);
+        if (c >= cA) break;
+        int out = OUT_NONE;
+        uint32_t s = 0;
+#if R3D_CHUNK_CLOCKS
+        const long long tc = clock64();
+#endif
+        const uint32_t j = c * 32u + lane;
+        if (j < nA) { s = q[j]; out = advance_one<Cell, TRACE>(M, J, A, tab, s, T); }
+        if (out == OUT_FREE) out = OUT_SRC;                     // list B: wants a new phonon in this iteration's phase 2
+        route<TRACE>(A, C, nxt, out, s);
+#if R3D_CHUNK_CLOCKS
+        if (lane == 0) { atomicAdd(&C.t_kind[0], (unsigned long long)(clock64() - tc)); atomicAdd(&C.n_kind[0], 1u); }
+#endif
+      }
+    }
+    __syncthreads();
     // ---- grant new phonons to the free slots: one atomic on the job's work counter per CTA per iteration ------
     if (threadIdx.x == 0) {
-      const uint32_t nf = C.cnt[cur * 2 + OUT_FREE];
+      const long long t1 = clock64(); C.t_phase[0] += (unsigned long long)(t1 - t0); t0 = t1;
+      const uint32_t nfa = C.cnt[cur * 2 + OUT_FREE], nfb = C.cnt[CNT_SRC], nf = nfa + nfb;
       uint32_t grant = 0;
       if (nf && !C.exhausted) {
         const unsigned long long b = atomicAdd(M.next_phonon, (unsigned long long)nf);
         if (b < J.n) { const unsigned long long left = J.n - b; grant = (left < nf) ? (uint32_t)left : nf; C.base = b; }
         if (grant < nf) C.exhausted = 1;
       }
-      C.granted = grant;
-      C.cnt[nxt * 2 + OUT_ADV] = 0; C.cnt[nxt * 2 + OUT_FREE] = 0;
-      C.cnt[CNT_SCAT] = 0; C.cnt[CNT_SRC] = 0; C.cnt[CNT_FP] = 0; C.cnt[CNT_FS] = 0; C.cnt[CNT_BEND] = 0;
-      C.cursor[0] = 0; C.cursor[1] = 0;
-      C.done = (C.cnt[cur * 2 + OUT_ADV] == 0 && grant == 0);
-      t0 = clock64();
+      C.grant_a = (grant < nfa) ? grant : nfa;
+      C.grant_b = grant - C.grant_a;
     }
     __syncthreads();
-    if (C.done) break;
 
-    // ---- phase 1: advance chunks, then refill chunks ---------------------------------------------------------
+    // ---- phase 2: face chunks (S, then P), then draw chunks (scatter, then new phonons), then bend chunks -----------
     {
-      const uint32_t nA = C.cnt[cur * 2 + OUT_ADV], nR = C.granted;
-      const uint32_t cA = (nA + 31u) >> 5, cR = (nR + 31u) >> 5;
-      const uint16_t *q = A.queue((uint32_t)cur);
-      const unsigned long long base = C.base;
-      for (;;) {
-        const uint32_t c = next_chunk(&C.cursor[0]);
-        if (c >= cA + cR) break;
-        int out = OUT_NONE;
-        uint32_t s = 0;
-#if R3D_CHUNK_CLOCKS
-        const long long tc = clock64();
-#endif
-        if (c < cA) {
-          const uint32_t j = c * 32u + lane;
-          if (j < nA) { s = q[j]; out = advance_one<Cell, TRACE>(M, J, A, tab, s, T); }
-        } else {
-          const uint32_t j = (c - cA) * 32u + lane;
-          if (j < nR) { s = q[S - 1u - j]; refill_one<TRACE>(M, J, A, s, base + j, T); out = OUT_SRC; }
-        }
-        route<TRACE>(A, C, nxt, out, s);
-#if R3D_CHUNK_CLOCKS
-        if (lane == 0) { const int kd = (c < cA) ? 0 : 1; atomicAdd(&C.t_kind[kd], (unsigned long long)(clock64() - tc)); atomicAdd(&C.n_kind[kd], 1u); }
-#endif
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { const long long t1 = clock64(); C.t_phase[0] += (unsigned long long)(t1 - t0); t0 = t1; }
-
-    // ---- phase 2: face chunks (S, then P), then draw chunks (scatter, then source), then bend chunks ---------------
-    {
-      const uint32_t nFS = C.cnt[CNT_FS], nFP = C.cnt[CNT_FP], nDS = C.cnt[CNT_SCAT], nDR = C.cnt[CNT_SRC];
+      const uint32_t nFS = C.cnt[CNT_FS], nFP = C.cnt[CNT_FP], nDS = C.cnt[CNT_SCAT], nGA = C.grant_a, nGB = C.grant_b;
       constexpr uint32_t DB = 32u * R3D_DRAW_U;                 // draws per chunk
       const uint32_t nB = C.cnt[CNT_BEND];
-      const uint32_t c0 = (nFS + 31u) >> 5, c1 = c0 + ((nFP + 31u) >> 5), c2 = c1 + (nDS + DB - 1u) / DB, c3 = c2 + (nDR + DB - 1u) / DB;
+      const uint32_t c0 = (nFS + 31u) >> 5, c1 = c0 + ((nFP + 31u) >> 5), c2 = c1 + (nDS + DB - 1u) / DB;
+      const uint32_t c2b = c2 + (nGA + DB - 1u) / DB, c3 = c2b + (nGB + DB - 1u) / DB;
       const uint32_t c4 = c3 + ((nB + 31u) >> 5);
       const uint16_t *qd = A.queue(2), *qf = A.queue(3), *qb = A.queue(4);
+      const uint16_t *qa = A.queue((uint32_t)cur);              // free lists: entry j of a list is q[S - 1 - j]
+      const unsigned long long base = C.base;
       for (;;) {
         const uint32_t c = next_chunk(&C.cursor[1]);
         if (c >= c4) break;
@@ -850,10 +858,19 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
           if (j < count) { s = qf[from_back ? S - 1u - j : j]; out = face_one<Cell, TRACE>(M, J, A, tab, s, T); }
           route<TRACE>(A, C, nxt, out, s);
         } else {
-          const bool is_src = c >= c2;
+          const bool is_src = c >= c2, list_b = c >= c2b;
+          const uint16_t *q = (is_src && !list_b) ? qa : qd;
+          const uint32_t j0 = (is_src ? (list_b ? c - c2b : c - c2) : c - c1) * DB, count = is_src ? (list_b ? nGB : nGA) : nDS;
+          if (is_src) {                       // new phonons first: index, ray type, request for the take-off angle
+#pragma unroll
+            for (int u = 0; u < R3D_DRAW_U; u++) {
+              const uint32_t j = j0 + (uint32_t)u * 32u + lane;
+              if (j < count) refill_one<TRACE>(M, J, A, q[S - 1u - j], base + (list_b ? nGA : 0u) + j, T);
+            }
+          }
           uint32_t s[R3D_DRAW_U];
           bool have[R3D_DRAW_U];
-          draw_batch<TRACE, R3D_DRAW_U>(M, J, A, qd, is_src, (is_src ? c - c2 : c - c1) * DB, is_src ? nDR : nDS, is_src, T, s, have);
+          draw_batch<TRACE, R3D_DRAW_U>(M, J, A, q, is_src, j0, count, is_src, T, s, have);
 #pragma unroll
           for (int u = 0; u < R3D_DRAW_U; u++) route<TRACE>(A, C, nxt, have[u] ? OUT_ADV : OUT_NONE, s[u]);
         }
