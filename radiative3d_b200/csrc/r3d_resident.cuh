@@ -15,10 +15,12 @@
 //   phase 1  advance  (slots ready to move)  time-out / validity checks, distance to boundary, path-length draw,
 //                                            move, cheap hand-overs inline; classification of the event; all draws the
 //                                            event will consume are taken from its Philox block here, in order
-//            refill   (free slots)           new phonon indices from the job's work counter; source ray type
+//   (between the phases: one atomicAdd on the job's work counter grants new phonon indices for the slots that phase 1 freed)
 //   phase 2  face     (queued face events)   seismometer catch through the uniform-grid index, R/T coefficients
 //            draw     (queued table draws)   exact guide-table CDF search + take-off-angle fetch from HBM/L2, then
-//                                            the new phonon's direction or Phonon::Transform
+//                                            Phonon::Transform; for a freed slot: the new phonon's index and ray type
+//                                            first, then its take-off angle and direction, in the same chunk - it
+//                                            advances in the next phase 1, like every other slot
 //            bend     (queued plain bends)   Snell bending at faces that neither collect nor reflect
 // Within a phase, warps pull 32-entry chunks of ONE kind of work from index queues in shared memory, so a warp
 // executes one kind of event (P and S face events are queued apart, source and scatter draws too).  State never
