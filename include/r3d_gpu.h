@@ -155,7 +155,7 @@ typedef struct r3d_model_desc {
   uint32_t faces_per_cell; /* R3D_*_NFACES matching cell_kind             */
   const double   *cell_params;     /* [n_cells][cell_nparam]              */
   const uint32_t *cell_scat;       /* [n_cells] scatterer index           */
-  const uint8_t  *face_flags;      /* [n_cells][faces_per_cell]           */
+  const uint8_t  *face_flags;      /* [n_cells][faces_per_cell] R3D_FACE_*; other bits are ignored */
   const uint32_t *face_other_cell; /* [n_cells][faces_per_cell]; ignored  */
                                    /*   unless R3D_FACE_ADJOIN is set     */
   double   cyl_radius2;    /* RCUCylinder::cmLossFace.mRad2 (cylinder only)*/

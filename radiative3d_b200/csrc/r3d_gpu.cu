@@ -434,11 +434,11 @@ int build_device(DevState &D, const r3d_model_desc *d) {
     // face: evaluated once here with the reference's own expression (plain IEEE double operations, no contraction
     // possible) and kept in two library-private bits of the flag byte, instead of two divisions per face crossing.
     std::vector<uint8_t> fl(d->face_flags, d->face_flags + nc * nf);
+    for (uint8_t &x : fl) x &= 0x0f;          // the ABI defines four bits (include/r3d_gpu.h:58-61)
     if (d->cell_kind == R3D_CELL_CYLINDER) {
       const size_t np = d->cell_nparam;
       for (size_t i = 0; i < nc; i++) for (size_t f = 0; f < nf; f++) {
         uint8_t &x = fl[i * nf + f];
-        x &= 0x0f;
         if (!(x & R3D_FACE_ADJOIN)) continue;
         const double *c = d->cell_params + i * np, *o = d->cell_params + (size_t)d->face_other_cell[i * nf + f] * np;
         volatile double dvp = std::fabs(2 * (o[0] - c[0]) / (o[0] + c[0])), dvs = std::fabs(2 * (o[1] - c[1]) / (o[1] + c[1]));
