@@ -14,7 +14,7 @@ def load(name):
         return json.loads(f.readline())
 
 
-@pytest.mark.parametrize("name", ["r1_bench.json", "r1_bench_4gpu.json", "r1_bench_8gpu.json"])
+@pytest.mark.parametrize("name", ["r1_bench.json", "r1_bench_2gpu.json", "r1_bench_4gpu.json", "r1_bench_8gpu.json"])
 def test_bench_line(name):
     d = load(name)
     for k in BASE:
