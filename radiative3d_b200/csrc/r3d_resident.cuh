@@ -34,6 +34,9 @@
 namespace r3d {
 
 #define R3D_FULL 0xffffffffu
+#ifndef R3D_MERGE_FACES
+#define R3D_MERGE_FACES 0      // 1: P and S face events share chunks (one partial chunk less per iteration, but every chunk then runs the S-only code too)
+#endif
 #define R3D_NT 512             // most threads per CTA of any cell kind (Cell::threads sets each kernel's launch bound, one CTA per SM)
 
 struct Job {
@@ -454,7 +457,7 @@ R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
         // collection and / or R/T and / or bending: phase 2.  For P only the outcome draw exists (k1).
         const uint32_t ka = (p.type == R3D_RAY_S) ? k1 : 0u, kb = (p.type == R3D_RAY_S) ? k2 : k1;
         A.req(s) = make_uint2(ka | ((uint32_t)(P.face & 1) << 31), kb | ((uint32_t)(P.face >> 1) << 31));
-        out = (action == FACE_BEND && !(fl & R3D_FACE_COLLECT)) ? OUT_BEND : (p.type == R3D_RAY_P) ? OUT_FP : OUT_FS;
+        out = (action == FACE_BEND && !(fl & R3D_FACE_COLLECT)) ? OUT_BEND : (R3D_MERGE_FACES || p.type == R3D_RAY_P) ? OUT_FP : OUT_FS;
       }
     }
   }
