@@ -34,6 +34,17 @@
 namespace r3d {
 
 #define R3D_FULL 0xffffffffu
+// R3D_CHECK=1 (make check -> libr3dgpu_check.so, tests/test_gpu_invariants.py): the queue invariants are asserted on the device
+// and a violation traps.  Two lists share a buffer from its two ends, and a slot that is taken out of a list leaves a stale
+// entry behind: an entry added to the same buffer for a slot that still has one there can make the ends meet - silently,
+// unless the model frees many slots per iteration (both times this happened only the halfspace runs crashed).
+#ifndef R3D_CHECK
+#define R3D_CHECK 0
+#endif
+__device__ __noinline__ void check_fail(int what, uint32_t a, uint32_t b) {
+  printf("r3d: queue invariant %d violated in block %d (%u, %u)\n", what, (int)blockIdx.x, a, b);
+  __trap();
+}
 #ifndef R3D_MERGE_FACES
 #define R3D_MERGE_FACES 0      // 1: P and S face events share chunks (one partial chunk less per iteration, but every chunk then runs the S-only code too)
 #endif
@@ -348,6 +359,7 @@ R3D_DEV void route(const Slots<TRACE> &A, Ctl &C, int nxt, int out, uint32_t s) 
   base = __shfl_sync(peers, base, leader);
   const uint32_t j = base + __popc(peers & ((1u << lane) - 1u));
   const uint32_t buf = (out < 2) ? (uint32_t)nxt : 1u + ((uint32_t)out >> 1);       // OUT_BEND = 6 -> buffer 4, from the front
+  if (R3D_CHECK && (j >= A.S || s >= A.S)) check_fail(1, j, s);
   A.queue(buf)[(out & 1) ? A.S - 1u - j : j] = (uint16_t)s;
 }
 
@@ -821,6 +833,14 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
     if (threadIdx.x == 0) {
       const long long t1 = clock64(); C.t_phase[0] += (unsigned long long)(t1 - t0); t0 = t1;
       const uint32_t nfa = C.cnt[cur * 2 + OUT_FREE], nfb = C.cnt[CNT_SRC], nf = nfa + nfb;
+      if (R3D_CHECK) {                       // the two ends of every buffer, after phase 1
+        if (C.cnt[nxt * 2 + OUT_ADV] + C.cnt[nxt * 2 + OUT_FREE] > S) check_fail(2, C.cnt[nxt * 2 + OUT_ADV], C.cnt[nxt * 2 + OUT_FREE]);
+        if (C.cnt[CNT_SCAT] + C.cnt[CNT_SRC] > S) check_fail(3, C.cnt[CNT_SCAT], C.cnt[CNT_SRC]);
+        if (C.cnt[CNT_FP] + C.cnt[CNT_FS] > S || C.cnt[CNT_BEND] > S) check_fail(4, C.cnt[CNT_FP] + C.cnt[CNT_FS], C.cnt[CNT_BEND]);
+        // every slot is in exactly one list (slots are only dropped once the job has no phonon left for them)
+        const uint32_t all = C.cnt[nxt * 2 + OUT_ADV] + C.cnt[nxt * 2 + OUT_FREE] + C.cnt[CNT_SCAT] + C.cnt[CNT_SRC] + C.cnt[CNT_FP] + C.cnt[CNT_FS] + C.cnt[CNT_BEND] + nfa;
+        if (C.exhausted ? all > S : all != S) check_fail(5, all, S);
+      }
       uint32_t grant = 0;
       if (nf && !C.exhausted) {
         const unsigned long long b = atomicAdd(M.next_phonon, (unsigned long long)nf);
@@ -885,7 +905,13 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0) { C.t_phase[1] += (unsigned long long)(clock64() - t0); C.iterations++; }
+    if (threadIdx.x == 0) {
+      C.t_phase[1] += (unsigned long long)(clock64() - t0); C.iterations++;
+      if (R3D_CHECK) {                       // after phase 2 every slot is ready to advance or free, in the next buffer
+        const uint32_t all = C.cnt[nxt * 2 + OUT_ADV] + C.cnt[nxt * 2 + OUT_FREE];
+        if (C.exhausted ? all > S : all != S) check_fail(6, C.cnt[nxt * 2 + OUT_ADV], C.cnt[nxt * 2 + OUT_FREE]);
+      }
+    }
     cur = nxt;
   }
   if (threadIdx.x == 0) {                    // warp time not spent inside chunks: barriers, waiting for a phase's last chunk
