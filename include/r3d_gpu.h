@@ -100,6 +100,8 @@ extern "C" {
 #define R3D_CNT_EVENTS   3   /* propagate-loop iterations (phonons.cpp:542), extension */
 #define R3D_CNT_CATCHES  4   /* bin updates (dataout.cpp:200-212), extension            */
 #define R3D_CNT_SCATTERS 5   /* scatter events (phonons.cpp:605-618), extension         */
+#define R3D_CNT_PHONONS  6   /* phonons generated (model.cpp:611-614), extension        */
+#define R3D_CNT_DIAG     7   /* DataReporter::mDiagInvalid: OR of (1 << R3D_INV_*); combined by OR, not by sum */
 #define R3D_NCOUNTERS    8
 
 /* invalid-phonon reasons, bit index into diag (dataout.hpp:229-237) */
@@ -200,7 +202,7 @@ typedef struct r3d_event {
   uint32_t type;       /* R3D_RAY_P / R3D_RAY_S                                 */
   uint32_t moves;      /* Phonon::mMoveCount ("it:")                            */
   uint32_t cell;       /* cell index (the reference prints the cell's address)  */
-  uint32_t reserved;
+  uint32_t reason;     /* R3D_EV_INV: bit mask (1 << R3D_INV_*) of the check that failed; else 0 */
   double   time, pathlen;
   double   loc[3];     /* model coordinates (the host applies ECS.OutConvert)   */
   double   theta, phi;

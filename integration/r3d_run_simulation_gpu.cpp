@@ -180,7 +180,12 @@ void Model::RunSimulation() {
           case R3D_EV_CEL: dataout.ReportCellToCell(P); break;
           case R3D_EV_LST: dataout.ReportLostPhonon(P); break;
           case R3D_EV_TMO: dataout.ReportPhononTimeout(P); break;
-          default:         dataout.ReportInvalidPhonon(P, DataReporter::INV_PATH_NAN); break;
+          default: {       // the reason only feeds mDiagInvalid (dataout.cpp:611-617)
+            int why = 0;
+            while (why < 6 && !((e.reason >> why) & 1u)) why++;
+            dataout.ReportInvalidPhonon(P, (DataReporter::invalid_reason_e)why);
+            break;
+          }
         }
       }
       std::cerr << (100 * (lo + n)) / nph << "% of " << nph << " have been cast.\n";

@@ -18,6 +18,12 @@
 //   R3D_HARNESS=randrun  same loop but with the C library generator seeded by
 //                      $R3D_HARNESS_SEED (statistical comparison runs).
 //   R3D_HARNESS=vectors  deterministic sub-kernel golden vectors.
+//   R3D_HARNESS_MUTATE=key=value,...  (any mode) after the reference built the Model, overwrite members of ITS objects
+//                      before flattening / running, so that the reference itself decides what a degenerate model does:
+//                      ttl, slow, loop (Phonon::cm_ttl / cm_slow_concern / cm_loop_concern), mfp_p, mfp_s (every
+//                      scatterer's mean free path), cyl_vel_p, cyl_vel_s (RCUCylinder::mVelTop), shell_c_p, shell_c_s
+//                      (SphereShell::mVelCoefC), shell_zr2_p, shell_zr2_s (SphereShell::mZeroRadius2).  Used for the invalid-phonon fixtures (phonons.cpp:554-584): no
+//                      stock model produces a single INV phonon.
 //   R3D_HARNESS=scatparams  the ScatterParams (nu eps a kappa el gam0) of every scatterer.
 //
 // Private members are reached with the usual "#define private public" trick,
@@ -111,6 +117,42 @@ extern "C" int rand(void) {
 }
 
 #include "r3d_flatten.hpp"   // shared with the product's reference-side stub (integration/)
+
+// R3D_HARNESS_MUTATE: see the header comment
+static void Mutate(Model & Mod, const char * spec) {
+  std::stringstream ss(spec);
+  std::string item;
+  while (std::getline(ss, item, ',')) {
+    size_t eq = item.find('=');
+    if (eq == std::string::npos) { std::cerr << "harness: bad mutation " << item << "\n"; exit(1); }
+    const std::string key = item.substr(0, eq);
+    const double v = strtod(item.c_str() + eq + 1, 0);
+    if (key == "ttl") Phonon::cm_ttl = v;
+    else if (key == "slow") Phonon::cm_slow_concern = v;
+    else if (key == "loop") Phonon::cm_loop_concern = (unsigned long)v;
+    else if (key == "mfp_p" || key == "mfp_s") {
+      for (Scatterer * s = Scatterer::cm_ll_first; s != 0; s = s->mpllNext) s->mMeanFreeP[key == "mfp_p" ? RAY_P : RAY_S] = v;
+    } else if (key == "cyl_vel_p" || key == "cyl_vel_s") {
+      for (size_t i = 0; i < Mod.mCellArray.size(); i++) {
+        RCUCylinder * c = dynamic_cast<RCUCylinder*>(Mod.mCellArray[i]);
+        if (!c) { std::cerr << "harness: " << key << " needs a cylinder model\n"; exit(1); }
+        c->mVelTop[key == "cyl_vel_p" ? RAY_P : RAY_S] = v;
+      }
+    } else if (key == "shell_c_p" || key == "shell_c_s") {
+      for (size_t i = 0; i < Mod.mCellArray.size(); i++) {
+        SphereShell * c = dynamic_cast<SphereShell*>(Mod.mCellArray[i]);
+        if (!c) { std::cerr << "harness: " << key << " needs a shell model\n"; exit(1); }
+        c->mVelCoefC[key == "shell_c_p" ? RAY_P : RAY_S] = v;
+      }
+    } else if (key == "shell_zr2_p" || key == "shell_zr2_s") {
+      for (size_t i = 0; i < Mod.mCellArray.size(); i++) {
+        SphereShell * c = dynamic_cast<SphereShell*>(Mod.mCellArray[i]);
+        if (!c) { std::cerr << "harness: " << key << " needs a shell model\n"; exit(1); }
+        c->mZeroRadius2[key == "shell_zr2_p" ? RAY_P : RAY_S] = v;
+      }
+    } else { std::cerr << "harness: unknown mutation " << key << "\n"; exit(1); }
+  }
+}
 
 // ---------------------------------------------------------------------------
 // result files
@@ -398,6 +440,7 @@ int main(int argc, char * argv[]) {
   }
   try {
     Model Mod(MParams);
+    if (const char * mut = getenv("R3D_HARNESS_MUTATE")) Mutate(Mod, mut);
     FlatModel F;
     Flatten(Mod, F);
     if (mode == "dump") {

@@ -78,7 +78,7 @@ EVENT_LABELS = ("GEN", "SCT", "COL", "REF", "CEL", "LST", "TMO", "INV")      # d
 
 # struct r3d_event
 EVENT_DTYPE = np.dtype([
-    ("phonon", "<u8"), ("seq", "<u4"), ("kind", "<u4"), ("type", "<u4"), ("moves", "<u4"), ("cell", "<u4"), ("reserved", "<u4"),
+    ("phonon", "<u8"), ("seq", "<u4"), ("kind", "<u4"), ("type", "<u4"), ("moves", "<u4"), ("cell", "<u4"), ("reason", "<u4"),
     ("time", "<f8"), ("pathlen", "<f8"), ("loc", "<f8", (3,)), ("theta", "<f8"), ("phi", "<f8"), ("amp", "<f8"),
 ])
 assert EVENT_DTYPE.itemsize == 96

@@ -86,11 +86,11 @@ __global__ void reduce_tally_kernel(const unsigned long long *rows, uint32_t n_r
   __shared__ unsigned long long sm[256];
   const int k = blockIdx.x;
   unsigned long long x = 0;
-  for (uint32_t r = threadIdx.x; r < n_rows; r += blockDim.x) { if (k == 7) x |= rows[(size_t)r * R3D_NCOUNTERS + k]; else x += rows[(size_t)r * R3D_NCOUNTERS + k]; }
+  for (uint32_t r = threadIdx.x; r < n_rows; r += blockDim.x) { if (k == R3D_CNT_DIAG) x |= rows[(size_t)r * R3D_NCOUNTERS + k]; else x += rows[(size_t)r * R3D_NCOUNTERS + k]; }
   sm[threadIdx.x] = x;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) { if (k == 7) sm[threadIdx.x] |= sm[threadIdx.x + o]; else sm[threadIdx.x] += sm[threadIdx.x + o]; }
+    if ((int)threadIdx.x < o) { if (k == R3D_CNT_DIAG) sm[threadIdx.x] |= sm[threadIdx.x + o]; else sm[threadIdx.x] += sm[threadIdx.x + o]; }
     __syncthreads();
   }
   if (threadIdx.x == 0) counters[k] = sm[0];
@@ -746,10 +746,10 @@ int r3d_fetch(r3d_handle *h, double *energies, uint64_t *counts, uint64_t *count
       }
     }
     CK(cudaMemcpy(k, D.M.counters, sizeof k, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < R3D_NCOUNTERS; i++) { if (i == 7) ksum[i] |= k[i]; else ksum[i] += k[i]; }
+    for (int i = 0; i < R3D_NCOUNTERS; i++) { if (i == R3D_CNT_DIAG) ksum[i] |= k[i]; else ksum[i] += k[i]; }
   }
   if (counters) for (int i = 0; i < R3D_NCOUNTERS; i++) counters[i] = ksum[i];
-  if (diag) *diag = (uint32_t)ksum[7];
+  if (diag) *diag = (uint32_t)ksum[R3D_CNT_DIAG];
   return 0;
 }
 
@@ -835,7 +835,7 @@ int r3d_kernel_times(r3d_handle *h, double seconds[3], uint64_t launches[3], uin
   seconds[2] = tot > 0 ? D.k_seconds * (double)c2 / tot : 0;  // of which phase 2 (table draws + face events)
   launches[0] = D.k_launches; launches[1] = it; launches[2] = (uint64_t)D.grid;
   units[0] = k[R3D_CNT_EVENTS];
-  units[1] = k[R3D_CNT_SCATTERS] + k[6];                      // table draws = scatter draws + source draws
+  units[1] = k[R3D_CNT_SCATTERS] + k[R3D_CNT_PHONONS];                      // table draws = scatter draws + source draws
   units[2] = k[R3D_CNT_CATCHES];
   return 0;
 }

@@ -78,7 +78,7 @@ struct Tally {
     v[R3D_CNT_LOST] += (f == R3D_FATE_LOST);
     v[R3D_CNT_TIMEOUT] += (f == R3D_FATE_TIMEOUT);
     v[R3D_CNT_INVALID] += (f == R3D_FATE_INVALID);
-    if (f == R3D_FATE_INVALID) v[7] |= (fate >> 8);
+    if (f == R3D_FATE_INVALID) v[R3D_CNT_DIAG] |= (fate >> 8);
   }
   // all threads of the CTA must call this
   R3D_DEV void flush(unsigned long long *row, unsigned long long (*sm)[R3D_NCOUNTERS]) {
@@ -86,15 +86,15 @@ struct Tally {
 #pragma unroll
     for (int k = 0; k < R3D_NCOUNTERS; k++) {
       unsigned long long x = v[k];
-      if (k == 7) { for (int o = 16; o > 0; o >>= 1) x |= __shfl_down_sync(R3D_FULL, x, o); }
+      if (k == R3D_CNT_DIAG) { for (int o = 16; o > 0; o >>= 1) x |= __shfl_down_sync(R3D_FULL, x, o); }
       else { for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(R3D_FULL, x, o); }
       if (lane == 0) sm[warp][k] = x;
     }
     __syncthreads();
     if (threadIdx.x < R3D_NCOUNTERS) {
       unsigned long long x = 0;
-      for (unsigned w = 0; w < nw; w++) { if (threadIdx.x == 7) x |= sm[w][threadIdx.x]; else x += sm[w][threadIdx.x]; }
-      if (x) { if (threadIdx.x == 7) row[threadIdx.x] |= x; else row[threadIdx.x] += x; }
+      for (unsigned w = 0; w < nw; w++) { if (threadIdx.x == R3D_CNT_DIAG) x |= sm[w][threadIdx.x]; else x += sm[w][threadIdx.x]; }
+      if (x) { if (threadIdx.x == R3D_CNT_DIAG) row[threadIdx.x] |= x; else row[threadIdx.x] += x; }
     }
   }
 };
@@ -238,14 +238,14 @@ R3D_DEV void write_final(const Slots<TRACE> &A, const Job &J, uint32_t s, const 
 // Event report (dataout.cpp:484-617): the phonon's state as output_phonon_dataline() prints it.  Trace mode only.
 template <bool TRACE>
 R3D_DEV void emit(const Slots<TRACE> &A, const Job &J, uint32_t s, uint32_t kind, int type, double time, double pathlen, v3 loc,
-                  v3 dir, double aexp, uint32_t cell, uint32_t moves) {
+                  v3 dir, double aexp, uint32_t cell, uint32_t moves, uint32_t reason = 0) {
   if (!TRACE) return;
   if (!J.events || !((J.event_mask >> kind) & 1u)) return;
   const uint32_t seq = A.tr(3, s)++;
   const unsigned long long at = atomicAdd(J.event_cursor, 1ull);
   if (at >= J.event_cap) return;
   r3d_event *e = J.events + at;
-  e->phonon = A.idx(s); e->seq = seq; e->kind = kind; e->type = (uint32_t)type; e->moves = moves; e->cell = cell; e->reserved = 0;
+  e->phonon = A.idx(s); e->seq = seq; e->kind = kind; e->type = (uint32_t)type; e->moves = moves; e->cell = cell; e->reason = reason;
   e->time = time; e->pathlen = pathlen; e->loc[0] = loc.x; e->loc[1] = loc.y; e->loc[2] = loc.z;
   angles_of(dir, e->theta, e->phi);
   e->amp = exp(-aexp);
@@ -479,7 +479,7 @@ R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
       if (!s1_loaded) { const double2 sxy = A.sxy(s); p.s1 = V(sxy.x, sxy.y, A.sz(s)); }
       const uint32_t f = fate & 0xFFu;
       emit<TRACE>(A, J, s, f == R3D_FATE_LOST ? R3D_EV_LST : f == R3D_FATE_TIMEOUT ? R3D_EV_TMO : R3D_EV_INV, p.type, p.time, p.pathlen,
-                  p.loc, p.dir, p.aexp, p.cell, p.moves);
+                  p.loc, p.dir, p.aexp, p.cell, p.moves, fate >> 8);
       write_final<TRACE>(A, J, s, p, fate, ordinal);
     }
     return OUT_FREE;
@@ -513,7 +513,7 @@ R3D_DEV void refill_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
   A.idx(s) = idx;
   A.meta(s) = make_uint4(0u, M.src_cell, 2u, (rt3 == R3D_RAY_P) ? R3D_RAY_P : R3D_RAY_S);
   if (TRACE) { A.tr(0, s) = 0; A.tr(1, s) = 0; A.tr(2, s) = 0; A.tr(3, s) = 0; }
-  T.v[6]++;
+  T.v[R3D_CNT_PHONONS]++;
 }
 
 // =====================================================================================================

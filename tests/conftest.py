@@ -20,9 +20,12 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
-def load_golden(cfg):
-    """(FlatModel, npz dict) of tests/golden/golden_<cfg>.npz (made from the reference by make_golden.py)."""
-    z = np.load(os.path.join(GOLDEN, f"golden_{cfg}.npz"))
+INV_CASES = ["path_nan", "time_nan", "path_negative", "stuck", "slow", "loop_exceed"]     # tests/golden/make_inv_golden.py
+
+
+def load_golden(cfg, prefix="golden"):
+    """(FlatModel, npz dict) of tests/golden/<prefix>_<cfg>.npz (made from the reference by make_golden.py / make_inv_golden.py)."""
+    z = np.load(os.path.join(GOLDEN, f"{prefix}_{cfg}.npz"))
     f, i = z["scalars_f"], z["scalars_i"]
     m = FlatModel(freq_hz=float(f[0]), ttl=float(f[1]), bin_dt=float(f[2]), earth_center=tuple(map(float, f[3:6])),
                   min_theta=float(f[6]), max_theta=float(f[7]), slow_concern=float(f[8]), src_loc=tuple(map(float, f[9:12])),

@@ -28,12 +28,16 @@ from make_golden import PLAN as MODEL_PLAN  # noqa: E402
 
 REF_MAIN = os.path.join(ROOT, "oracle", "_ref", "r3d_ref_main")
 WINDOWS = 10          # time windows per seismometer
-# config -> (processes, phonons per process)
+# fixture -> (workload, take-off-angle degree (None: that of golden_<workload>.npz), processes, phonons per process)
 PLAN = {
-    "halfspace": (16, 1_000_000),
-    "crustpinch": (16, 20_000),
-    "lopnor": (16, 20_000),
-    "spherical": (16, 1_200),
+    "halfspace": ("halfspace", None, 16, 1_000_000),
+    "halfspace_nearsrc50": ("halfspace_nearsrc50", None, 16, 1_000_000),
+    "crustpinch": ("crustpinch", None, 16, 20_000),
+    "lopnor": ("lopnor", None, 16, 20_000),
+    "spherical": ("spherical", None, 16, 1_200),
+    # the benchmarked configuration itself (bench.py): the scripted degree 9, 5 242 880 take-off angles; the GPU test builds
+    # the same model on the box with the reference's host code (integration/_build/r3d_gpu_main)
+    "halfspace_nearsrc50_deg9": ("halfspace_nearsrc50", 9, 16, 1_000_000),
 }
 
 
@@ -91,19 +95,20 @@ def windows(a, w=WINDOWS):
 def main():
     if not os.path.exists(REF_MAIN):
         sys.exit("oracle/_ref/r3d_ref_main is missing: run `make -C oracle ref` where /root/reference exists")
-    for cfg in (sys.argv[1:] or list(PLAN)):
-        procs, n_each = PLAN[cfg]
-        deg = MODEL_PLAN[cfg][0]
+    for name in (sys.argv[1:] or list(PLAN)):
+        cfg, deg, procs, n_each = PLAN[name]
+        if deg is None:
+            deg = MODEL_PLAN[cfg][0]
         t = time.time()
         with tempfile.TemporaryDirectory() as tmp:
             res = run_batch(cfg, deg, procs, n_each, tmp)
         counts = np.stack([windows(c) for c, _, _ in res]).astype(np.int64)          # [P, n_seis, W, 2]
         energy = np.stack([windows(e) for _, e, _ in res])                           # [P, n_seis, W, 2]
         counters = np.array([k for _, _, k in res], dtype=np.int64)                   # [P, 3] lost, timeout, invalid
-        path = os.path.join(HERE, f"stat_{cfg}.npz")
+        path = os.path.join(HERE, f"stat_{name}.npz")
         np.savez_compressed(path, counts=counts, energy=energy.astype(np.float32), counters=counters,
                             n_each=np.int64(n_each), toa_degree=np.int64(deg), windows=np.int64(WINDOWS))
-        print(f"stat_{cfg}.npz: {procs} x {n_each} phonons, {int(counts.sum())} catches, counters {counters.sum(axis=0)}, "
+        print(f"stat_{name}.npz: {cfg} at TOA degree {deg}, {procs} x {n_each} phonons, {int(counts.sum())} catches, counters {counters.sum(axis=0)}, "
               f"{os.path.getsize(path) / 1e3:.0f} kB, {time.time() - t:.0f} s")
 
 

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_binding as ob
-from conftest import CONFIGS, GOLDEN, dense_bins, load_golden, rel_err
+from conftest import CONFIGS, GOLDEN, INV_CASES, dense_bins, load_golden, rel_err
 from radiative3d_b200 import abi
 
 TOL = 1e-12   # relative; the north-star bar for deterministic sub-kernels is 1e-10
@@ -103,6 +103,25 @@ def test_whole_run(cfg):
     assert rel_err(e, e_ref).max() <= 1e-9
     assert np.array_equal(k[:3], z["run_counters"][:3])
     assert int(k[abi.R3D_CNT_PHONONS]) == n
+
+
+@pytest.mark.parametrize("case", INV_CASES)
+def test_invalid_phonons(case):
+    """Row a22: the seven validity checks (phonons.cpp:554-584) on models the reference itself ran after the harness made
+    them degenerate (tests/golden/make_inv_golden.py): mNumInvalid, mDiagInvalid and every end state, NaNs included."""
+    m, z = load_golden(case, prefix="inv")
+    n, seed = int(z["run_n"]), int(z["run_seed"])
+    e, c, k, fin = ob.run(m, 0, n, seed, finals=True)
+    ref, kr = z["run_finals"], z["run_counters"]
+    assert int(kr[abi.R3D_CNT_INVALID]) > 0 and int(kr[abi.R3D_CNT_DIAG]) != 0
+    assert np.array_equal(k[:3], kr[:3]) and int(k[abi.R3D_CNT_DIAG]) == int(kr[abi.R3D_CNT_DIAG])
+    for f in ("moves", "cell", "type", "fate", "draws"):
+        assert np.array_equal(fin[f], ref[f]), f
+    for f in ("time", "pathlen", "amp", "theta", "phi", "pol", "loc"):
+        assert rel_err(fin[f], ref[f]).max() <= TOL, f
+    e_ref, c_ref = dense_bins(m, z)
+    assert np.array_equal(c, c_ref)
+    assert e.size == 0 or rel_err(e, e_ref).max() <= 1e-9          # (time_nan has no seismometers)
 
 
 def test_threads_match_serial():
