@@ -286,6 +286,15 @@ typedef struct r3d_scatter_params {
   double nu, eps, a, kappa;   /* density/velocity scaling, RMS perturbation, correlation distance, von Karman parameter */
   double el, gam0;            /* S wavenumber omega / beta0, Vp / Vs                                                   */
 } r3d_scatter_params;
+/* The pieces of r3d_build_scatterer_tables for a host program that keeps the reference's own ProbDist objects (the drop-in
+ * program's Scatterer::PopulateProbDists, integration/r3d_scatterer_gpu.cpp): upload the take-off angles once, then get the
+ * un-integrated G values g[4][n_toa] (gpp, gps, gsp, gss) and the S->S polarisation angles spol[n_toa] of one parameter
+ * set per call; the host integrates them itself (ProbDist::Integrate). */
+typedef struct r3d_toa_set r3d_toa_set;
+int  r3d_toa_create(const double *toa_theta, const double *toa_phi, uint32_t n_toa, int device, r3d_toa_set **out);
+int  r3d_scatterer_g_values(r3d_toa_set *t, const r3d_scatter_params *par, double *g, double *spol);
+void r3d_toa_destroy(r3d_toa_set *t);
+
 /* For each of the n_par parameter sets: cdf[p][4][n_toa] (PP,PS,SP,SS, cumulative), spol[p][n_toa], whole_cdf[p][2][4]
  * (cumulative, as r3d_model_desc.scat_whole_cdf), mfp[p][2]; all host arrays, laid out as r3d_model_desc wants them.
  * The take-off angles are uploaded once; uses CUDA device `device`. */

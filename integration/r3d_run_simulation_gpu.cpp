@@ -19,14 +19,17 @@
 // phonon by phonon as in the reference).  Their side effects - the seismometer scan of ReportPhononCollected and the
 // loss counters - are switched off around the printing, because the GPU already did both.
 //
-// Environment (all optional):
-//   R3D_GPU_DEVICES=0,1,...   CUDA devices to shard the phonon index range over   (default: 0)
-//   R3D_GPU_SEED=<u64>        Philox seed (default: time(NULL), like the reference's srand(time(NULL)))
-//   R3D_GPU_NUM_PHONONS=<u64> 64-bit phonon count, overrides --num-phonons (the reference's is an int)
-//   R3D_GPU_CHECKPOINT=<path> after every tenth of the run write bins + counters + the phonon-index watermark to <path>;
+// Options (r3d_cli.hpp, parsed by r3d_main.cpp before the reference's parser; each also has the environment form of round 1):
+//   --gpu-devices=0,1,...     CUDA devices to shard the phonon index range over   (default: 0)
+//   --seed=<u64>              Philox seed (default: time(NULL), like the reference's srand(time(NULL)))
+//   --num-phonons=<u64>       64-bit phonon count with the reference's K / M / B suffixes (the reference's is an int)
+//   --gpu-checkpoint=<path>   after every tenth of the run write bins + counters + the phonon-index watermark to <path>;
 //                             if <path> exists and belongs to the same run (count, seed, bin layout), continue from its
 //                             watermark.  Phonon i always uses draw stream (seed, i), so a resumed run equals an
 //                             uninterrupted one (the reference can only "resume" by adding another run, combine.m).
+//                             Without --seed the seed is taken from the checkpoint; a checkpoint of another run (count,
+//                             seed or bin layout) is an error, never silently overwritten.
+// Environment (testing / tooling):
 //   R3D_GPU_STOP_AFTER=<k>    stop after k tenths (testing the checkpoint)
 //   R3D_GPU_DUMP_MODEL=<path> also write the flattened model (include/r3d_modelfile.h)
 //   R3D_GPU_DUMP_ONLY=1       ... and return without simulating
@@ -59,23 +62,39 @@
 
 #include "r3d_modelfile.h"
 #include "r3d_flatten.hpp"
+#include "r3d_cli.hpp"
 
 namespace {
 // checkpoint file: header, then energies f64, counts u64, counters u64
 struct CkptHeader { char magic[8]; uint64_t nph, seed, watermark, n_seis, n_bins; };
-bool ckpt_read(const char * path, uint64_t nph, uint64_t seed, size_t ns, size_t nb, uint64_t & watermark,
+// true: resumed.  false: no checkpoint file.  A file that is not a checkpoint of THIS run is an error (it would be overwritten).
+// `seed` is taken from the header when the user gave none.
+bool ckpt_read(const char * path, uint64_t nph, uint64_t & seed, bool have_seed, size_t ns, size_t nb, uint64_t & watermark,
                std::vector<double> & e, std::vector<uint64_t> & c, std::vector<uint64_t> & k) {
   FILE * f = fopen(path, "rb");
   if (!f) return false;
   CkptHeader hd;
-  bool ok = fread(&hd, sizeof hd, 1, f) == 1 && memcmp(hd.magic, "R3DCKPT1", 8) == 0 && hd.nph == nph && hd.seed == seed &&
-            hd.n_seis == ns && hd.n_bins == nb && hd.watermark <= nph;
+  if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, "R3DCKPT1", 8) != 0) {
+    fclose(f);
+    throw Runtime(std::string("checkpoint file ") + path + " exists but is not an r3d checkpoint; remove it or choose another path");
+  }
+  if (!have_seed) seed = hd.seed;
+  if (hd.nph != nph || hd.seed != seed || hd.n_seis != ns || hd.n_bins != nb || hd.watermark > nph) {
+    fclose(f);
+    std::ostringstream msg;
+    msg << "checkpoint file " << path << " belongs to another run (its phonons / seed / seismometers x bins: " << hd.nph << " / "
+        << hd.seed << " / " << hd.n_seis << " x " << hd.n_bins << "; this run: " << nph << " / " << seed << " / " << ns << " x " << nb
+        << "); remove it or choose another path";
+    throw Runtime(msg.str());
+  }
+  bool ok = true;
   ok = ok && fread(e.data(), sizeof(double), ns * nb * R3D_BIN_NF64, f) == ns * nb * R3D_BIN_NF64;
   ok = ok && fread(c.data(), sizeof(uint64_t), ns * nb * R3D_BIN_NCNT, f) == ns * nb * R3D_BIN_NCNT;
   ok = ok && fread(k.data(), sizeof(uint64_t), R3D_NCOUNTERS, f) == R3D_NCOUNTERS;
   fclose(f);
-  if (ok) watermark = hd.watermark;
-  return ok;
+  if (!ok) throw Runtime(std::string("checkpoint file ") + path + " is truncated; remove it");
+  watermark = hd.watermark;
+  return true;
 }
 void ckpt_write(const char * path, uint64_t nph, uint64_t seed, size_t ns, size_t nb, uint64_t watermark,
                 const std::vector<double> & e, const std::vector<uint64_t> & c, const std::vector<uint64_t> & k) {
@@ -98,6 +117,18 @@ void r3d_check(int rc, const char * what) {
 }
 }
 
+// ModelParams::OutputOctaveText (model.cpp:138-...), called by the reference's main() before the model is built: the
+// reference parses --num-phonons with atoi() into an int (cmdline.cpp:366-384) although ModelParams::NumPhonons is a long.
+// model.cpp is compiled with -DOutputOctaveText=OutputOctaveText_reference_cpu (integration/Makefile), so this definition is
+// the one main() reaches: it writes the file with the reference's own code from a copy that holds the true 64-bit count,
+// so that NumPhonons in out_mparams.octv stays what vis/seisplot/combine.m:31-33 adds up.
+void r3d_mparams_octave_reference(const ModelParams *, std::ostream *) asm("_ZNK11ModelParams30OutputOctaveText_reference_cpuEPSo");
+void ModelParams::OutputOctaveText(std::ostream * out) const {
+  ModelParams copy(*this);
+  if (r3d_cli::options().have_nph) copy.NumPhonons = (long)r3d_cli::options().nph;
+  r3d_mparams_octave_reference(&copy, out);
+}
+
 void Model::RunSimulation() {
 
   FlatModel F;
@@ -109,17 +140,12 @@ void Model::RunSimulation() {
     if (getenv("R3D_GPU_DUMP_ONLY")) return;
   }
 
-  std::vector<int> devices;
-  if (const char * s = getenv("R3D_GPU_DEVICES")) {
-    std::stringstream ss(s);
-    std::string tok;
-    while (std::getline(ss, tok, ',')) if (!tok.empty()) devices.push_back(atoi(tok.c_str()));
-  }
+  const r3d_cli::Options & opt = r3d_cli::options();
+  std::vector<int> devices = opt.devices;
   if (devices.empty()) devices.push_back(0);
-  uint64_t seed = (uint64_t)time(NULL);
-  if (const char * s = getenv("R3D_GPU_SEED")) seed = strtoull(s, 0, 0);
+  uint64_t seed = opt.have_seed ? opt.seed : (uint64_t)time(NULL);
   uint64_t nph = (mNumPhonons > 0) ? (uint64_t)mNumPhonons : 0;
-  if (const char * s = getenv("R3D_GPU_NUM_PHONONS")) nph = strtoull(s, 0, 0);
+  if (opt.have_nph) nph = opt.nph;
 
   r3d_handle * h = 0;
   r3d_check(r3d_create(&F.d, devices.data(), (int)devices.size(), &h), "r3d_create");
@@ -151,7 +177,8 @@ void Model::RunSimulation() {
     const unsigned long keep_lost = dataout.mNumLost, keep_tmo = dataout.mNumTimeout, keep_inv = dataout.mNumInvalid;
     const unsigned keep_diag = dataout.mDiagInvalid;
     const uint64_t batch = 4096;
-    std::vector<r3d_event> ev(batch * 256);
+    std::vector<r3d_event> ev(batch * 64);
+    bool retraced = false;
     Phonon P(S2::ThetaPhi(0, 0), RAY_P);
     for (uint64_t lo = 0; lo < nph; lo += batch) {
       const uint64_t n = std::min<uint64_t>(batch, nph - lo);
@@ -160,8 +187,11 @@ void Model::RunSimulation() {
         int rc = r3d_trace_events(h, lo, n, seed, ev_mask, ev.data(), ev.size(), &got);
         if (rc != 0) { std::string msg = r3d_last_error(); r3d_destroy(h); throw Runtime("GPU propagate path: " + msg); }
         if (got <= ev.size()) break;
-        r3d_destroy(h);
-        throw Runtime("GPU propagate path: more than 256 events per phonon on average; shorten --timetolive for report runs");
+        // More events than room (the whole-Earth model reports ~220 per phonon at its scripted time to live): make room and
+        // trace the batch again.  Every trace also accumulates into the device bins; the bins of a report run therefore
+        // come from a separate plain pass over the same phonons after the printing (below), not from these traces.
+        ev.resize(got + got / 8 + 1024);
+        retraced = true;
       }
       for (uint64_t i = 0; i < got; i++) {
         const r3d_event & e = ev[i];
@@ -190,13 +220,19 @@ void Model::RunSimulation() {
       }
       std::cerr << (100 * (lo + n)) / nph << "% of " << nph << " have been cast.\n";
     }
+    if (retraced) {         // a batch was traced twice: take bins and counters from one plain pass (same phonons, same draws)
+      int rc = r3d_reset(h);
+      if (rc == 0) rc = r3d_run(h, 0, nph, seed);
+      if (rc == 0) rc = r3d_sync(h, 0);
+      if (rc != 0) { std::string msg = r3d_last_error(); r3d_destroy(h); throw Runtime("GPU propagate path: " + msg); }
+    }
     seis_keep.swap(dataout.mSeismometers);
     dataout.mNumLost = keep_lost; dataout.mNumTimeout = keep_tmo; dataout.mNumInvalid = keep_inv; dataout.mDiagInvalid = keep_diag;
   } else {
-  const char * ckpt = getenv("R3D_GPU_CHECKPOINT");
+  const char * ckpt = opt.checkpoint.empty() ? 0 : opt.checkpoint.c_str();
   const int stop_after = getenv("R3D_GPU_STOP_AFTER") ? atoi(getenv("R3D_GPU_STOP_AFTER")) : 10;
   uint64_t watermark = 0;
-  if (ckpt && ckpt_read(ckpt, nph, seed, ns, nb, watermark, e0, c0, k0))
+  if (ckpt && ckpt_read(ckpt, nph, seed, opt.have_seed, ns, nb, watermark, e0, c0, k0))
     std::cerr << "r3d-gpu: resuming from checkpoint " << ckpt << " at phonon " << watermark << "\n";
   else { std::fill(e0.begin(), e0.end(), 0.0); std::fill(c0.begin(), c0.end(), 0); std::fill(k0.begin(), k0.end(), 0); watermark = 0; }
   for (int slice = 0; slice < 10; slice++) {
@@ -217,7 +253,7 @@ void Model::RunSimulation() {
       r3d_check(r3d_fetch(h, e.data(), c.data(), k.data(), &dg), "r3d_fetch");
       for (size_t i = 0; i < e.size(); i++) e[i] += e0[i];
       for (size_t i = 0; i < c.size(); i++) c[i] += c0[i];
-      for (int i = 0; i < R3D_NCOUNTERS; i++) { if (i == 7) k[i] |= k0[i]; else k[i] += k0[i]; }
+      for (int i = 0; i < R3D_NCOUNTERS; i++) { if (i == R3D_CNT_DIAG) k[i] |= k0[i]; else k[i] += k0[i]; }
       ckpt_write(ckpt, nph, seed, ns, nb, hi, e, c, k);
     }
     if (slice + 1 >= stop_after && slice + 1 < 10) {
@@ -239,8 +275,8 @@ void Model::RunSimulation() {
   r3d_destroy(h);
   for (size_t i = 0; i < e.size(); i++) e[i] += e0[i];
   for (size_t i = 0; i < c.size(); i++) c[i] += c0[i];
-  for (int i = 0; i < R3D_NCOUNTERS; i++) { if (i == 7) k[i] |= k0[i]; else k[i] += k0[i]; }
-  diag |= (uint32_t)k0[7];
+  for (int i = 0; i < R3D_NCOUNTERS; i++) { if (i == R3D_CNT_DIAG) k[i] |= k0[i]; else k[i] += k0[i]; }
+  diag |= (uint32_t)k0[R3D_CNT_DIAG];
   bool clipped = false;
   for (size_t s = 0; s < ns; s++) {
     Seismometer & S = *dataout.mSeismometers[s];

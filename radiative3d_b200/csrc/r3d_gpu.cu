@@ -37,6 +37,13 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
                   std::string(#call) + ": " + cudaGetErrorString(e_));                             \
   } while (0)
 
+// The public entry points select the device they work on; the caller's current device is put back on return.
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 // ---------------------------------------------------------------------------
 // model-preparation kernels
 // ---------------------------------------------------------------------------
@@ -658,6 +665,7 @@ const char *r3d_last_error(void) { return g_err.c_str(); }
 int r3d_abi_version(void) { return R3D_ABI_VERSION; }
 
 int r3d_create(const r3d_model_desc *desc, const int *devices, int n_dev, r3d_handle **out) {
+  DeviceGuard guard;
   if (!out) return fail(R3D_EINVAL, "null output handle");
   *out = nullptr;
   if (int rc = validate(desc)) return rc;
@@ -682,6 +690,7 @@ int r3d_create(const r3d_model_desc *desc, const int *devices, int n_dev, r3d_ha
 }
 
 void r3d_destroy(r3d_handle *h) {
+  DeviceGuard guard;
   if (!h) return;
   for (DevState *D : h->devs) destroy_device(D);
   delete h;
@@ -715,6 +724,7 @@ int r3d_sync(r3d_handle *h, double *device_seconds) {
 }
 
 int r3d_fetch(r3d_handle *h, double *energies, uint64_t *counts, uint64_t *counters, uint32_t *diag) {
+  DeviceGuard guard;
   if (!h) return fail(R3D_EINVAL, "null handle");
   const size_t nb = (size_t)h->n_seis * h->n_bins;
   std::vector<double> e;
@@ -754,6 +764,7 @@ int r3d_fetch(r3d_handle *h, double *energies, uint64_t *counts, uint64_t *count
 }
 
 int r3d_reset(r3d_handle *h) {
+  DeviceGuard guard;
   if (!h) return fail(R3D_EINVAL, "null handle");
   const size_t nb = std::max<size_t>((size_t)h->n_seis * h->n_bins, 1);
   for (DevState *Dp : h->devs) {
@@ -792,6 +803,7 @@ int r3d_launch_count(r3d_handle *h, uint64_t *n) {
 }
 
 int r3d_set_profiling(r3d_handle *h, int on) {
+  DeviceGuard guard;
   if (!h) return fail(R3D_EINVAL, "null handle");
   (void)on;                                 // the kernel is always timed; this call resets the totals
   for (DevState *D : h->devs) {
@@ -806,6 +818,7 @@ int r3d_set_profiling(r3d_handle *h, int on) {
 }
 
 int r3d_kernel_times(r3d_handle *h, double seconds[3], uint64_t launches[3], uint64_t units[3]) {
+  DeviceGuard guard;
   if (!h || !seconds || !launches || !units) return fail(R3D_EINVAL, "null argument");
   DevState &D = *h->devs[0];
   if (int rc = drain(D)) return rc;
@@ -841,6 +854,7 @@ int r3d_kernel_times(r3d_handle *h, double seconds[3], uint64_t launches[3], uin
 }
 
 int r3d_trace(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons, uint64_t seed, r3d_phonon_final *out) {
+  DeviceGuard guard;
   if (!h || !out) return fail(R3D_EINVAL, "null argument");
   if (!n_phonons) return 0;
   DevState &D = *h->devs[0];
@@ -861,6 +875,7 @@ int r3d_trace(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons, uint64_t
 
 int r3d_trace_events(r3d_handle *h, uint64_t first_phonon, uint64_t n_phonons, uint64_t seed, uint32_t kinds_mask,
                      r3d_event *out, uint64_t capacity, uint64_t *n_events) {
+  DeviceGuard guard;
   if (!h || !n_events || (capacity && !out)) return fail(R3D_EINVAL, "null argument");
   *n_events = 0;
   if (!n_phonons) return 0;
@@ -912,6 +927,7 @@ int need_device() {
   return 0;
 }
 int path_hook(r3d_handle *h, const double *in, uint32_t n, double *out, int advance_mode) {
+  DeviceGuard guard;
   if (!h || !in || !out) return fail(R3D_EINVAL, "null argument");
   DevState &D = *h->devs[0];
   if (int rc = drain(D)) return rc;
@@ -947,37 +963,75 @@ int rows_hook(K launch_fn, const double *in, uint32_t n, int win, int wout, doub
 
 extern "C" {
 
+// ---- scatterer tables ----------------------------------------------------------------------------------
+}  // extern "C"
+struct r3d_toa_set {
+  int device = 0;
+  uint32_t n = 0;
+  double *th = nullptr, *ph = nullptr, *g = nullptr, *spol = nullptr;      // device: angles, G values [4][n], polarisation angles
+};
+extern "C" {
+
+int r3d_toa_create(const double *toa_theta, const double *toa_phi, uint32_t n_toa, int device, r3d_toa_set **out) {
+  if (!toa_theta || !toa_phi || !n_toa || !out) return fail(R3D_EINVAL, "null argument");
+  *out = nullptr;
+  if (int rc = need_device()) return rc;
+  DeviceGuard guard;
+  CK(cudaSetDevice(device));
+  r3d_toa_set *t = new r3d_toa_set();
+  t->device = device; t->n = n_toa;
+  const size_t n = n_toa;
+  cudaError_t e = cudaMalloc(&t->th, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&t->ph, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&t->g, 4 * n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&t->spol, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(t->th, toa_theta, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(t->ph, toa_phi, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { r3d_toa_destroy(t); return fail(e == cudaErrorMemoryAllocation ? R3D_ENOMEM : R3D_ECUDA, std::string("r3d_toa_create: ") + cudaGetErrorString(e)); }
+  *out = t;
+  return 0;
+}
+
+void r3d_toa_destroy(r3d_toa_set *t) {
+  if (!t) return;
+  DeviceGuard guard;
+  cudaSetDevice(t->device);
+  cudaFree(t->th); cudaFree(t->ph); cudaFree(t->g); cudaFree(t->spol);
+  delete t;
+}
+
+int r3d_scatterer_g_values(r3d_toa_set *t, const r3d_scatter_params *par, double *g, double *spol) {
+  if (!t || !par || !g || !spol) return fail(R3D_EINVAL, "null argument");
+  DeviceGuard guard;
+  CK(cudaSetDevice(t->device));
+  const r3d_scatter_params &P = *par;
+  const size_t n = t->n;
+  // PSATO's numerator does not depend on the angle (scatparams.cpp:184-188)
+  const double numer = (8. * pow(kPi, 1.5) * P.eps * P.eps * P.a * P.a * P.a) * tgamma(P.kappa + 1.5) / tgamma(P.kappa);
+  gsato_kernel<<<(unsigned)((n + 255) / 256), 256>>>(P, numer, t->th, t->ph, t->n, t->g, t->spol);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(g, t->g, 4 * n * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(spol, t->spol, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int r3d_build_scatterer_tables(const r3d_scatter_params *par, uint32_t n_par, const double *toa_theta, const double *toa_phi,
                                uint32_t n_toa, int device, double *cdf, double *spol, double *whole_cdf, double *mfp) {
   if (!par || !toa_theta || !toa_phi || !n_toa || !cdf || !spol || !whole_cdf || !mfp) return fail(R3D_EINVAL, "null argument");
-  if (int rc = need_device()) return rc;
-  CK(cudaSetDevice(device));
-  Scratch S;
-  double *dth, *dph, *dg, *dsp;
+  r3d_toa_set *t = nullptr;
+  if (int rc = r3d_toa_create(toa_theta, toa_phi, n_toa, device, &t)) return rc;
   const size_t n = n_toa;
-  if (int rc = S.up(toa_theta, n, &dth)) return rc;
-  if (int rc = S.up(toa_phi, n, &dph)) return rc;
-  if (int rc = S.up((const double *)nullptr, 4 * n, &dg)) return rc;
-  if (int rc = S.up((const double *)nullptr, n, &dsp)) return rc;
   for (uint32_t p = 0; p < n_par; p++) {
-    const r3d_scatter_params &P = par[p];
     double *c = cdf + (size_t)p * 4 * n, *w = whole_cdf + (size_t)p * 8;
-    // PSATO's numerator does not depend on the angle (scatparams.cpp:184-188)
-    const double numer = (8. * pow(kPi, 1.5) * P.eps * P.eps * P.a * P.a * P.a) * tgamma(P.kappa + 1.5) / tgamma(P.kappa);
-    gsato_kernel<<<(unsigned)((n + 255) / 256), 256>>>(P, numer, dth, dph, n_toa, dg, dsp);
-    CK(cudaGetLastError());
+    if (int rc = r3d_scatterer_g_values(t, par + p, c, spol + (size_t)p * n)) { std::string keep = g_err; r3d_toa_destroy(t); g_err = keep; return rc; }
     // ProbDist::Integrate (probability.cpp:21-35): the running sum in index order decides table indices, so it is formed on
-    // the host exactly as the reference forms it; each table is summed by its own thread while the next one is copied back
+    // the host exactly as the reference forms it (one thread per table)
     std::thread scan[4];
-    cudaError_t e = cudaSuccess;
-    for (int t = 0; t < 4 && e == cudaSuccess; t++) {
-      double *ct = c + (size_t)t * n;
-      e = cudaMemcpy(ct, dg + (size_t)t * n, n * sizeof(double), cudaMemcpyDeviceToHost);
-      if (e == cudaSuccess) scan[t] = std::thread([ct, n] { for (size_t i = 1; i < n; i++) ct[i] += ct[i - 1]; });
+    for (int k = 0; k < 4; k++) {
+      double *ct = c + (size_t)k * n;
+      scan[k] = std::thread([ct, n] { for (size_t i = 1; i < n; i++) ct[i] += ct[i - 1]; });
     }
-    if (e == cudaSuccess) e = cudaMemcpy(spol + (size_t)p * n, dsp, n * sizeof(double), cudaMemcpyDeviceToHost);
-    for (int t = 0; t < 4; t++) if (scan[t].joinable()) scan[t].join();
-    if (e != cudaSuccess) return fail(R3D_ECUDA, std::string("r3d_build_scatterer_tables: ") + cudaGetErrorString(e));
+    for (int k = 0; k < 4; k++) scan[k].join();
     const double tot[4] = {c[n - 1], c[2 * n - 1], c[3 * n - 1], c[4 * n - 1]};
     // PopulateWholeProbs (scatterers.cpp:170-183), integrated: IN_P = {gpp, gps, 0, 0}, IN_S = {0, 0, gsp, gss}
     w[0] = tot[0]; w[1] = tot[0] + tot[1]; w[2] = w[1] + 0.0; w[3] = w[2] + 0.0;
@@ -986,6 +1040,7 @@ int r3d_build_scatterer_tables(const r3d_scatter_params *par, uint32_t n_par, co
     mfp[2 * p + 0] = 1.0 / (w[3] / (double)n_toa);
     mfp[2 * p + 1] = 1.0 / (w[7] / (double)n_toa);
   }
+  r3d_toa_destroy(t);
   return 0;
 }
 

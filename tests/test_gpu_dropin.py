@@ -54,27 +54,34 @@ def test_reference_program_with_gpu_loop(cfg, deg, n, tmp_path):
 
 
 def test_checkpoint_and_resume(tmp_path):
-    """R3D_GPU_CHECKPOINT: a run stopped after 4 tenths and resumed equals the uninterrupted run (phonon i always uses
-    draw stream (seed, i)): counts and loss counters exactly, energies up to summation order."""
+    """--gpu-checkpoint: a run stopped after 4 tenths and resumed equals the uninterrupted run (phonon i always uses draw
+    stream (seed, i)): counts and loss counters exactly, energies up to summation order.  The resumed run is started
+    WITHOUT --seed and takes it from the checkpoint; a checkpoint of another run is refused, not overwritten."""
     if not os.path.exists(reference_host.GPU_MAIN):
         pytest.skip("integration/_build/r3d_gpu_main was not built (needs the reference checkout at build time)")
     import subprocess
     from radiative3d_b200 import workloads
     cfg, deg, n, seed = "halfspace", 4, 400000, 99
 
-    def run(outdir, **extra):
+    def run(outdir, *opts, count=n, **extra):
         os.makedirs(outdir, exist_ok=True)
-        env = dict(os.environ, R3D_GPU_SEED=str(seed), **extra)
-        return subprocess.run([reference_host.GPU_MAIN] + workloads.cmdline(cfg, n, deg, str(outdir)), cwd=str(outdir), env=env,
-                              capture_output=True, text=True)
+        return subprocess.run([reference_host.GPU_MAIN] + workloads.cmdline(cfg, count, deg, str(outdir)) + list(opts), cwd=str(outdir),
+                              env=dict(os.environ, **extra), capture_output=True, text=True)
 
-    whole = run(tmp_path / "whole")
+    whole = run(tmp_path / "whole", f"--seed={seed}")
     assert whole.returncode == 0
     ck = str(tmp_path / "run.ckpt")
-    part = run(tmp_path / "resumed", R3D_GPU_CHECKPOINT=ck, R3D_GPU_STOP_AFTER="4")
+    part = run(tmp_path / "resumed", f"--seed={seed}", f"--gpu-checkpoint={ck}", R3D_GPU_STOP_AFTER="4")
     assert part.returncode == 3 and os.path.exists(ck)
-    rest = run(tmp_path / "resumed", R3D_GPU_CHECKPOINT=ck)
-    assert rest.returncode == 0 and "resuming from checkpoint" in rest.stderr
+    before = open(ck, "rb").read()
+    # another run must not take the file over: different phonon count, and different seed
+    other = run(tmp_path / "other", f"--seed={seed}", f"--gpu-checkpoint={ck}", count=n + 1)
+    assert other.returncode == 1 and "belongs to another run" in other.stdout + other.stderr
+    other = run(tmp_path / "other", f"--seed={seed + 1}", f"--gpu-checkpoint={ck}")
+    assert other.returncode == 1 and "belongs to another run" in other.stdout + other.stderr
+    assert open(ck, "rb").read() == before
+    rest = run(tmp_path / "resumed", f"--gpu-checkpoint={ck}")                # no --seed: taken from the checkpoint
+    assert rest.returncode == 0 and "resuming from checkpoint" in rest.stderr and f"seed {seed}" in rest.stderr
     summary = lambda p: re.findall(r"(Loss surfaces|Timeout|Invalidity):\s+(\d+)", p.stdout)
     assert summary(whole) == summary(rest)
     for i in (0, 70, 143):
@@ -82,3 +89,28 @@ def test_checkpoint_and_resume(tmp_path):
         b = read_octv(os.path.join(tmp_path / "resumed", f"seis_{i:03d}.octv"))
         assert np.array_equal(a["CountPS"], b["CountPS"])
         assert np.allclose(a["TracePS"], b["TracePS"], rtol=1e-5, atol=0)
+
+
+def test_command_line_options_of_the_gpu_path(tmp_path):
+    """--num-phonons with the reference's K suffix read as a 64-bit count, --seed, --gpu-devices (integration/r3d_cli.hpp):
+    the run equals the same range through the ABI, and out_mparams.octv carries the count (model.cpp:148-150)."""
+    if not os.path.exists(reference_host.GPU_MAIN):
+        pytest.skip("integration/_build/r3d_gpu_main was not built (needs the reference checkout at build time)")
+    import subprocess
+    from radiative3d_b200 import workloads
+    cfg, deg, seed = "halfspace_nearsrc50", 3, 31337
+    args = [a for a in workloads.cmdline(cfg, 10, deg, str(tmp_path)) if not a.startswith("--num-phonons")]
+    args += ["-N", "250K", f"--seed={seed}", "--gpu-devices", "0", "--mparams-outfile=out_mparams.octv"]
+    p = subprocess.run([reference_host.GPU_MAIN] + args, cwd=str(tmp_path), capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "250000 phonons on 1 device(s)" in p.stderr and f"seed {seed}" in p.stderr
+    txt = open(os.path.join(tmp_path, "out_mparams.octv")).read()
+    assert re.search(r"# name: NumPhonons \n# type: scalar \n250000 ", txt)
+    m = reference_host.build_model(cfg, deg)
+    with engine.Engine(m) as eng:
+        eng.run_simulation(250000, seed=seed)
+        e, c, k = eng.fetch()
+    got = tuple(int(re.search(rf"{name}:\s+(\d+)", p.stdout).group(1)) for name in ("Loss surfaces", "Timeout", "Invalidity"))
+    assert got == tuple(int(x) for x in k[:3])
+    o = read_octv(os.path.join(tmp_path, "seis_010.octv"))
+    assert np.array_equal(o["CountPS"].astype(np.uint64), c[10])

@@ -24,7 +24,7 @@ import pytest
 
 from conftest import GOLDEN, load_golden
 
-CONFIGS = ["halfspace", "crustpinch", "lopnor", "spherical"]
+CONFIGS = ["halfspace", "halfspace_nearsrc50", "crustpinch", "lopnor", "spherical"]
 
 
 def windows(a, w):
