@@ -20,6 +20,12 @@
  * ABI.  Every function returning int returns 0 on success and a non-zero
  * R3D_E* code otherwise; r3d_last_error() then holds a message (thread-local).
  * All descriptor arrays are BORROWED for the duration of r3d_create only.
+ * The five large tables of a descriptor (toa_theta, toa_phi, src_cdf, scat_cdf,
+ * scat_spol) may live in host memory (pinned memory makes the upload direct)
+ * or in DEVICE memory of any CUDA device of the process - e.g. a buffer that a
+ * multi-process launcher received by an NCCL broadcast over NVLink, so that
+ * the tables cross PCIe once per node and not once per GPU; all other arrays
+ * are read by the host and must be host memory.
  * There is no CPU fallback: with no usable CUDA device r3d_create fails.
  */
 #ifndef R3D_GPU_H_
@@ -32,7 +38,7 @@
 extern "C" {
 #endif
 
-#define R3D_ABI_VERSION 1
+#define R3D_ABI_VERSION 2
 
 /* error codes */
 #define R3D_OK            0
@@ -103,6 +109,8 @@ extern "C" {
 #define R3D_CNT_PHONONS  6   /* phonons generated (model.cpp:611-614), extension        */
 #define R3D_CNT_DIAG     7   /* DataReporter::mDiagInvalid: OR of (1 << R3D_INV_*); combined by OR, not by sum */
 #define R3D_NCOUNTERS    8
+#define R3D_NDIAG_LANES  8   /* 0/1 lanes of the diagnostic word's bits, kept after the counters on the device (see
+                              * r3d_device_accumulator_blocks) */
 
 /* invalid-phonon reasons, bit index into diag (dataout.hpp:229-237) */
 #define R3D_INV_PATH_NAN      0
@@ -212,7 +220,9 @@ typedef struct r3d_event {
 typedef struct r3d_handle r3d_handle;
 
 /* Upload a model to `n_dev` CUDA devices (replicated) and allocate
- * zeroed bins.  devices==NULL means device 0..n_dev-1. */
+ * zeroed bins.  devices==NULL means device 0..n_dev-1.  With several devices
+ * the host arrays are uploaded once, to the first device; the others copy the
+ * large tables from its memory (NVLink peer copies). */
 int r3d_create(const r3d_model_desc *desc, const int *devices, int n_dev,
                r3d_handle **out);
 
@@ -231,7 +241,12 @@ int r3d_sync(r3d_handle *h, double *device_seconds);
 
 /* Synchronise, sum over the handle's devices, copy out.  Any pointer may be
  * NULL.  energies: [n_seis][n_bins][5] f64; counts: [n_seis][n_bins][2] u64;
- * counters: [R3D_NCOUNTERS]; diag: OR of (1<<R3D_INV_*). */
+ * counters: [R3D_NCOUNTERS]; diag: OR of (1<<R3D_INV_*).
+ * The sum over the devices of a handle (the reference's combine.m:26-33) is
+ * made ON THE DEVICE: a kernel on the first device reads the other devices'
+ * accumulators through peer access (NVLink) in device order and writes the
+ * sums to a staging buffer, which is then copied to the host once.  Devices
+ * that are not peers are summed on the host instead. */
 int r3d_fetch(r3d_handle *h, double *energies, uint64_t *counts,
               uint64_t *counters, uint32_t *diag);
 
@@ -244,6 +259,16 @@ int r3d_reset(r3d_handle *h);
  * u64[n_seis*n_bins*2], counters u64[R3D_NCOUNTERS] (diag is counters[7]). */
 int r3d_device_accumulators(r3d_handle *h, int dev_slot, void **energies,
                             void **counts, void **counters);
+
+/* The same accumulators as TWO blocks, so that a multi-process launcher needs two collectives (one per element type) and no
+ * host synchronisation: f64_block = the energies (n_f64 doubles); i64_block (n_i64 u64 words) = counts
+ * [n_seis*n_bins*2], then at word *counters_at the counters [R3D_NCOUNTERS], then R3D_NDIAG_LANES lanes holding bit b of
+ * the diagnostic word as 0 / 1.  After a SUM all-reduce of i64_block every word is right except counters[R3D_CNT_DIAG]
+ * (a sum of bit masks): rebuild it as OR over b of (lane[b] != 0) << b (radiative3d_b200/distributed.py does this on the
+ * device).  In-place reduction is for the END of a run: the next r3d_run recomputes the counters from the device's own
+ * tallies, so call r3d_fetch (and r3d_reset before any further r3d_run) right after it. */
+int r3d_device_accumulator_blocks(r3d_handle *h, int dev_slot, void **f64_block, uint64_t *n_f64, void **i64_block,
+                                  uint64_t *n_i64, uint64_t *counters_at);
 
 /* The CUDA stream r3d_run launches on for `dev_slot` (a cudaStream_t). */
 int r3d_stream(r3d_handle *h, int dev_slot, void **stream);

@@ -22,7 +22,8 @@
 //                      before flattening / running, so that the reference itself decides what a degenerate model does:
 //                      ttl, slow, loop (Phonon::cm_ttl / cm_slow_concern / cm_loop_concern), mfp_p, mfp_s (every
 //                      scatterer's mean free path), cyl_vel_p, cyl_vel_s (RCUCylinder::mVelTop), shell_c_p, shell_c_s
-//                      (SphereShell::mVelCoefC), shell_zr2_p, shell_zr2_s (SphereShell::mZeroRadius2).  Used for the invalid-phonon fixtures (phonons.cpp:554-584): no
+//                      (SphereShell::mVelCoefC), shell_zr2_p, shell_zr2_s (SphereShell::mZeroRadius2), no_reflect=1
+//                      (CellFace::mReflect cleared on every reflecting face).  Used for the invalid-phonon fixtures (phonons.cpp:554-584): no
 //                      stock model produces a single INV phonon.
 //   R3D_HARNESS=scatparams  the ScatterParams (nu eps a kappa el gam0) of every scatterer.
 //
@@ -150,6 +151,10 @@ static void Mutate(Model & Mod, const char * spec) {
         if (!c) { std::cerr << "harness: " << key << " needs a shell model\n"; exit(1); }
         c->mZeroRadius2[key == "shell_zr2_p" ? RAY_P : RAY_S] = v;
       }
+    } else if (key == "no_reflect") {        // every reflecting face stops reflecting: phonons that reach the free surface are lost
+      for (size_t i = 0; i < Mod.mCellArray.size(); i++)
+        for (Index f = 0; f < Mod.mCellArray[i]->NumFaces(); f++)
+          if (Mod.mCellArray[i]->Face(f).IsReflectionFace()) Mod.mCellArray[i]->Face(f).SetReflect(v == 0);
     } else { std::cerr << "harness: unknown mutation " << key << "\n"; exit(1); }
   }
 }

@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-R3D_ABI_VERSION = 1
+R3D_ABI_VERSION = 2
 
 R3D_RAY_P, R3D_RAY_S, R3D_RAY_SH, R3D_RAY_SV = 0, 1, 1, 2
 R3D_CELL_CYLINDER, R3D_CELL_TETRA, R3D_CELL_SHELL = 0, 1, 2
@@ -20,7 +20,10 @@ R3D_CNT_LOST, R3D_CNT_TIMEOUT, R3D_CNT_INVALID = 0, 1, 2
 R3D_CNT_EVENTS, R3D_CNT_CATCHES, R3D_CNT_SCATTERS = 3, 4, 5
 R3D_CNT_PHONONS, R3D_CNT_DIAG = 6, 7
 R3D_NCOUNTERS = 8
+R3D_NDIAG_LANES = 8
 R3D_FATE_LOST, R3D_FATE_TIMEOUT, R3D_FATE_INVALID = 1, 2, 3
+(R3D_INV_PATH_NAN, R3D_INV_TIME_NAN, R3D_INV_PATH_NEGATIVE, R3D_INV_TIME_NEGATIVE, R3D_INV_STUCK, R3D_INV_SLOW,
+ R3D_INV_LOOP_EXCEED) = range(7)
 
 _pd = C.POINTER(C.c_double)
 _pu32 = C.POINTER(C.c_uint32)

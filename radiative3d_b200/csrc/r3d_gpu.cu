@@ -100,7 +100,33 @@ __global__ void reduce_tally_kernel(const unsigned long long *rows, uint32_t n_r
     if ((int)threadIdx.x < o) { if (k == R3D_CNT_DIAG) sm[threadIdx.x] |= sm[threadIdx.x + o]; else sm[threadIdx.x] += sm[threadIdx.x + o]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) counters[k] = sm[0];
+  if (threadIdx.x == 0) {
+    counters[k] = sm[0];
+    if (k == R3D_CNT_DIAG)                     // one 0/1 lane per reason bit, after the counters (sums of lanes survive an all-reduce)
+      for (int b = 0; b < R3D_NDIAG_LANES; b++) counters[R3D_NCOUNTERS + b] = (sm[0] >> b) & 1ull;
+  }
+}
+
+// Sum of the accumulators of the devices of one handle, by a kernel on device slot 0 that reads its peers' memory over
+// NVLink (devices in slot order, so the sums have the bits a host loop over the devices would produce).
+#define R3D_MAX_PEERS 16
+struct PeerPtrs { const void *p[R3D_MAX_PEERS]; int n; };
+__global__ void combine_f64_kernel(PeerPtrs P, size_t n, double *out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double v = static_cast<const double *>(P.p[0])[i];
+    for (int g = 1; g < P.n; g++) v += static_cast<const double *>(P.p[g])[i];
+    out[i] = v;
+  }
+}
+__global__ void combine_u64_kernel(PeerPtrs P, size_t n, size_t or_index, unsigned long long *out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned long long v = static_cast<const unsigned long long *>(P.p[0])[i];
+    for (int g = 1; g < P.n; g++) {
+      const unsigned long long x = static_cast<const unsigned long long *>(P.p[g])[i];
+      if (i == or_index) v |= x; else v += x;
+    }
+    out[i] = v;
+  }
 }
 
 // ScatterParams::GSATO with XSATO and PSATO inlined (scatparams.cpp:75-194); one take-off angle per thread.
@@ -238,6 +264,13 @@ struct DevState {
   unsigned long long launches = 0;
   double k_seconds = 0;                    // device time of the propagate kernel alone since r3d_set_profiling
   unsigned long long k_launches = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};    // job begin / end, kernel begin / end (made once per device)
+  // the integer accumulators are one allocation, so that a launcher can all-reduce them with ONE collective:
+  // counts [n_seis*n_bins*2] | counters [R3D_NCOUNTERS] | diag lanes [R3D_NDIAG_LANES] (lane b = 1 if bit b of the diagnostic
+  // word is set: lanes survive a SUM all-reduce, the OR-combined word does not)
+  unsigned long long *ibuf = nullptr;
+  size_t n_ibuf = 0, n_fbuf = 0;
+  const double *raw_theta = nullptr, *raw_phi = nullptr, *raw_spol = nullptr;   // the take-off angles and S->S angles as given (sources of peer copies)
 };
 
 }  // namespace
@@ -245,16 +278,47 @@ struct DevState {
 struct r3d_handle {
   std::vector<DevState *> devs;
   uint32_t cell_kind = 0, n_seis = 0, n_bins = 0;
+  // in-process multi-device handles: the devices' accumulators are summed by a kernel on device slot 0 that reads the
+  // other devices' memory over NVLink (peer access), into these staging buffers; one device-to-host copy follows
+  bool peer_ok = false;
+  double *sum_f64 = nullptr;
+  unsigned long long *sum_i64 = nullptr;
 };
 
 namespace {
 
-// Device memory comes from the device's stream-ordered pool, whose release threshold is raised at r3d_create so that a
-// destroy -> create cycle (one per run of the host program's loop) reuses the memory instead of going to the driver.
+// Device memory comes from a stream-ordered pool PRIVATE to this library (one per device, made on first use and kept for
+// the life of the process, release threshold = never), so that a destroy -> create cycle (one per run of the host
+// program's loop) reuses the memory instead of going to the driver - and the device's default pool, which other code of
+// the process may use, keeps its own settings.
+constexpr int kMaxDevices = 64;
+cudaMemPool_t g_pool[kMaxDevices];
+bool g_pool_made[kMaxDevices];
+std::mutex g_pool_mu;
+int device_pool(int dev, cudaMemPool_t *out) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (dev < 0 || dev >= kMaxDevices) return fail(R3D_ENODEV, "device index out of range");
+  if (!g_pool_made[dev]) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    CK(cudaMemPoolCreate(&g_pool[dev], &props));
+    unsigned long long keep = ~0ull;
+    CK(cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+    g_pool_made[dev] = true;
+  }
+  *out = g_pool[dev];
+  return 0;
+}
 template <class T>
 int dev_alloc(DevState &D, T **p, size_t count) {
   void *q = nullptr;
-  CK(cudaMallocAsync(&q, std::max<size_t>(count, 1) * sizeof(T), D.stream));
+  cudaMemPool_t pool;
+  if (int rc = device_pool(D.device, &pool)) return rc;
+  CK(cudaMallocFromPoolAsync(&q, std::max<size_t>(count, 1) * sizeof(T), pool, D.stream));
   D.allocs.push_back(q);
   *p = static_cast<T *>(q);
   return 0;
@@ -263,7 +327,7 @@ template <class T>
 int dev_upload(DevState &D, const T **p, const T *host, size_t count) {
   T *q = nullptr;
   if (int rc = dev_alloc(D, &q, count)) return rc;
-  if (count) CK(cudaMemcpyAsync(q, host, count * sizeof(T), cudaMemcpyHostToDevice, D.stream));
+  if (count) CK(cudaMemcpyAsync(q, host, count * sizeof(T), cudaMemcpyDefault, D.stream));   // host memory, or device memory of any device
   *p = q;
   return 0;
 }
@@ -383,12 +447,7 @@ int env_int(const char *name, int dflt) {
 int build_device(DevState &D, const r3d_model_desc *d) {
   CK(cudaSetDevice(D.device));
   CK(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
-  {
-    cudaMemPool_t pool;
-    CK(cudaDeviceGetDefaultMemPool(&pool, D.device));
-    unsigned long long keep = ~0ull;
-    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  }
+  for (int i = 0; i < 4; i++) CK(cudaEventCreate(&D.ev[i]));
   const bool timing = env_int("R3D_TIMING", 0) != 0;
   auto t_start = std::chrono::steady_clock::now();
   auto lap = [&](const char *what) {
@@ -418,6 +477,7 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   if (int rc = dev_alloc(D, &toa, nt)) return rc;
   pack_toa_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, D.stream>>>(th, ph, toa, (uint32_t)nt, d->min_theta, d->max_theta);
   M.toa = toa;
+  D.raw_theta = th; D.raw_phi = ph;
 
   lap("stream, pool, toa");
   if (int rc = dev_upload(D, &M.src_cdf, d->src_cdf, 3 * nt)) return rc;
@@ -431,6 +491,7 @@ int build_device(DevState &D, const r3d_model_desc *d) {
     if (int rc = dev_alloc(D, &spol, ns * nt)) return rc;
     pack_spol_kernel<<<(unsigned)((ns * nt + 255) / 256), 256, 0, D.stream>>>(spol_raw, spol, ns * nt);
     M.scat_spol = spol;
+    D.raw_spol = spol_raw;
   }
   lap("cdf tables, spol");
   if (int rc = dev_upload(D, &M.cell_params, d->cell_params, nc * d->cell_nparam)) return rc;
@@ -500,13 +561,15 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   lap("monotone check, guide tables");
   // accumulators
   const size_t nb = std::max<size_t>((size_t)d->n_seis * d->n_bins, 1);
-  if (int rc = dev_alloc(D, &M.energies, nb * R3D_BIN_NF64)) return rc;
-  if (int rc = dev_alloc(D, &M.counts, nb * R3D_BIN_NCNT)) return rc;
-  if (int rc = dev_alloc(D, &M.counters, (size_t)R3D_NCOUNTERS)) return rc;
+  D.n_fbuf = nb * R3D_BIN_NF64;
+  D.n_ibuf = nb * R3D_BIN_NCNT + R3D_NCOUNTERS + R3D_NDIAG_LANES;
+  if (int rc = dev_alloc(D, &M.energies, D.n_fbuf)) return rc;
+  if (int rc = dev_alloc(D, &D.ibuf, D.n_ibuf)) return rc;
+  M.counts = D.ibuf;
+  M.counters = D.ibuf + nb * R3D_BIN_NCNT;
   if (int rc = dev_alloc(D, &M.next_phonon, (size_t)1)) return rc;
-  CK(cudaMemsetAsync(M.energies, 0, nb * R3D_BIN_NF64 * sizeof(double), D.stream));
-  CK(cudaMemsetAsync(M.counts, 0, nb * R3D_BIN_NCNT * sizeof(unsigned long long), D.stream));
-  CK(cudaMemsetAsync(M.counters, 0, R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
+  CK(cudaMemsetAsync(M.energies, 0, D.n_fbuf * sizeof(double), D.stream));
+  CK(cudaMemsetAsync(D.ibuf, 0, D.n_ibuf * sizeof(unsigned long long), D.stream));
 
   lap("accumulators");
   // launch geometry: persistent CTAs, `blocks_per_sm` per SM, each with an equal share of the SM's shared memory
@@ -550,32 +613,36 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   return 0;
 }
 
-// One job on one device (called on the device's worker thread): one launch of the persistent kernel.
+// One job on one device (called on the device's worker thread): one launch of the persistent kernel - or several, for a
+// job of more than kMaxPerLaunch phonons: a slot keeps its phonon's index relative to the launch's first phonon in 32 bits,
+// and the per-thread tallies are 32-bit (a thread sees phonons / (CTAs x threads) of a launch, so 2^30 phonons per launch
+// leave room for 2 x 10^5 loop events per phonon on average).
+constexpr unsigned long long kMaxPerLaunch = 1ull << 30;
 int run_job(DevState &D, const JobReq &jr) {
   CK(cudaSetDevice(D.device));
-  cudaEvent_t ev0, ev1, ek0, ek1;
-  CK(cudaEventCreate(&ev0));
-  CK(cudaEventCreate(&ev1));
-  CK(cudaEventCreate(&ek0));
-  CK(cudaEventCreate(&ek1));
+  cudaEvent_t ev0 = D.ev[0], ev1 = D.ev[1], ek0 = D.ev[2], ek1 = D.ev[3];
   CK(cudaEventRecord(ev0, D.stream));
-  if (jr.n) {
-    const bool trace = jr.finals != nullptr || jr.events != nullptr;
-    Job J; J.first = jr.first; J.n = jr.n; J.seed = jr.seed; J.finals = jr.finals;
+  const bool trace = jr.finals != nullptr || jr.events != nullptr;
+  unsigned long long n_launch = 0;
+  for (unsigned long long done = 0; done < jr.n;) {
+    const unsigned long long n = std::min(jr.n - done, kMaxPerLaunch);
+    Job J; J.first = jr.first + done; J.n = n; J.seed = jr.seed; J.finals = jr.finals ? jr.finals + done : nullptr;
     J.events = jr.events; J.event_cursor = jr.event_cursor; J.event_cap = jr.event_cap; J.event_mask = jr.event_mask;
     // no more slots than phonons: a small job is spread over all CTAs instead of filling the first few
     uint32_t S = D.max_slots[trace ? 1 : 0];
-    const unsigned long long share = (jr.n + (unsigned long long)D.grid - 1) / (unsigned long long)D.grid;
+    const unsigned long long share = (n + (unsigned long long)D.grid - 1) / (unsigned long long)D.grid;
     if (share < S) S = (uint32_t)((share + 31ull) / 32ull * 32ull);
     const size_t smem = (size_t)S * (trace ? R3D_SLOT_BYTES_TRACE : R3D_SLOT_BYTES) + D.table_bytes;
-    const unsigned long long need = (jr.n + S - 1) / S;
+    const unsigned long long need = (n + S - 1) / S;
     const int grid = (int)std::min<unsigned long long>((unsigned long long)D.grid, need);
     CK(cudaMemsetAsync(D.M.next_phonon, 0, sizeof(unsigned long long), D.stream));
-    CK(cudaEventRecord(ek0, D.stream));
+    if (!n_launch) CK(cudaEventRecord(ek0, D.stream));
     pick_propagate(D.cell_kind, trace, D.table_bytes != 0)<<<grid, D.threads, smem, D.stream>>>(D.M, J, S, D.table_bytes, D.block_tally, D.block_clock);
-    CK(cudaEventRecord(ek1, D.stream));
     D.launches += 1;
+    n_launch++;
+    done += n;
   }
+  if (n_launch) CK(cudaEventRecord(ek1, D.stream));
   reduce_tally_kernel<<<R3D_NCOUNTERS, 256, 0, D.stream>>>(D.block_tally, (uint32_t)D.grid, D.M.counters);
   D.launches += 1;
   CK(cudaEventRecord(ev1, D.stream));
@@ -583,12 +650,11 @@ int run_job(DevState &D, const JobReq &jr) {
   CK(cudaGetLastError());
   float ms = 0, kms = 0;
   CK(cudaEventElapsedTime(&ms, ev0, ev1));
-  if (jr.n) CK(cudaEventElapsedTime(&kms, ek0, ek1));
-  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ek0); cudaEventDestroy(ek1);
+  if (n_launch) CK(cudaEventElapsedTime(&kms, ek0, ek1));
   {
     std::lock_guard<std::mutex> lk(D.mu);
     D.seconds += ms * 1e-3;
-    if (jr.n) { D.k_seconds += kms * 1e-3; D.k_launches += 1; }
+    if (n_launch) { D.k_seconds += kms * 1e-3; D.k_launches += n_launch; }
   }
   return 0;
 }
@@ -649,6 +715,7 @@ void destroy_device(DevState *D) {
     if (D->stream) cudaStreamSynchronize(D->stream);
     for (void *p : D->allocs) cudaFreeAsync(p, D->stream);
     if (D->stream) cudaStreamSynchronize(D->stream);
+    for (int i = 0; i < 4; i++) if (D->ev[i]) cudaEventDestroy(D->ev[i]);
     if (D->stream) cudaStreamDestroy(D->stream);
   }
   delete D;
@@ -676,14 +743,50 @@ int r3d_create(const r3d_model_desc *desc, const int *devices, int n_dev, r3d_ha
   if (n_dev <= 0) return fail(R3D_EINVAL, "n_dev must be >= 1");
   r3d_handle *h = new r3d_handle();
   h->cell_kind = desc->cell_kind; h->n_seis = desc->n_seis; h->n_bins = desc->n_bins;
+  auto bail = [&](int rc) { std::string keep = g_err; r3d_destroy(h); g_err = keep; return rc; };
+  // Several devices: the host arrays cross PCIe ONCE, to device slot 0; the other devices copy the large tables from
+  // slot 0's memory (NVLink when the devices are peers, else staged by the driver) and derive their own packed tables
+  // and guides.  Peer access in both directions between slot 0 and every other slot also serves r3d_fetch's sum.
+  r3d_model_desc from0 = *desc;
+  bool peers = n_dev > 1 && n_dev <= R3D_MAX_PEERS && env_int("R3D_PEER_COMBINE", 1) != 0;
   for (int i = 0; i < n_dev; i++) {
     int dev = devices ? devices[i] : i;
     if (dev < 0 || dev >= count) { r3d_destroy(h); return fail(R3D_ENODEV, "device index out of range"); }
+    for (int j = 0; j < i; j++) if (h->devs[j]->device == dev) { r3d_destroy(h); return fail(R3D_EINVAL, "device listed twice"); }
     DevState *D = new DevState();
     h->devs.push_back(D);
     D->device = dev;
-    if (int rc = build_device(*D, desc)) { std::string keep = g_err; r3d_destroy(h); g_err = keep; return rc; }
+    if (int rc = build_device(*D, i == 0 ? desc : &from0)) return bail(rc);
+    if (i == 0 && n_dev > 1 && env_int("R3D_PEER_REPLICATE", 1) != 0) {
+      from0.toa_theta = D->raw_theta; from0.toa_phi = D->raw_phi; from0.src_cdf = D->M.src_cdf;
+      from0.scat_cdf = D->M.scat_cdf; from0.scat_spol = D->raw_spol;
+    }
+    if (i > 0 && peers) {
+      const int d0 = h->devs[0]->device;
+      int a = 0, b = 0;
+      if (cudaDeviceCanAccessPeer(&a, d0, dev) != cudaSuccess || cudaDeviceCanAccessPeer(&b, dev, d0) != cudaSuccess || !a || !b) peers = false;
+      else {
+        cudaMemPool_t p0, pi;
+        if (int rc = device_pool(d0, &p0)) return bail(rc);
+        if (int rc = device_pool(dev, &pi)) return bail(rc);
+        cudaMemAccessDesc acc;
+        acc.flags = cudaMemAccessFlagsProtReadWrite;
+        acc.location.type = cudaMemLocationTypeDevice;
+        acc.location.id = d0;
+        if (cudaMemPoolSetAccess(pi, &acc, 1) != cudaSuccess) peers = false;       // slot 0 reads this device's accumulators
+        acc.location.id = dev;
+        if (cudaMemPoolSetAccess(p0, &acc, 1) != cudaSuccess) peers = false;       // (and this device may read slot 0's tables)
+        cudaGetLastError();
+      }
+    }
     D->worker = std::thread(worker_main, D);
+  }
+  if (peers) {
+    DevState &D0 = *h->devs[0];
+    if (cudaSetDevice(D0.device) != cudaSuccess) return bail(fail(R3D_ECUDA, "cudaSetDevice"));
+    if (int rc = dev_alloc(D0, &h->sum_f64, D0.n_fbuf)) return bail(rc);
+    if (int rc = dev_alloc(D0, &h->sum_i64, D0.n_ibuf)) return bail(rc);
+    h->peer_ok = true;
   }
   *out = h;
   return 0;
@@ -727,36 +830,59 @@ int r3d_fetch(r3d_handle *h, double *energies, uint64_t *counts, uint64_t *count
   DeviceGuard guard;
   if (!h) return fail(R3D_EINVAL, "null handle");
   const size_t nb = (size_t)h->n_seis * h->n_bins;
-  std::vector<double> e;
-  std::vector<unsigned long long> c;
   unsigned long long k[R3D_NCOUNTERS], ksum[R3D_NCOUNTERS] = {0};
-  if (h->devs.empty()) {                       // (the first device's copy below overwrites; nothing to clear otherwise)
+  if (h->devs.empty()) {
     if (energies) memset(energies, 0, nb * R3D_BIN_NF64 * sizeof(double));
     if (counts) memset(counts, 0, nb * R3D_BIN_NCNT * sizeof(uint64_t));
   }
-  for (size_t g = 0; g < h->devs.size(); g++) {
-    DevState &D = *h->devs[g];
-    if (int rc = drain(D)) return rc;
-    CK(cudaSetDevice(D.device));
-    CK(cudaStreamSynchronize(D.stream));
-    if (energies && nb) {
-      if (g == 0) CK(cudaMemcpy(energies, D.M.energies, nb * R3D_BIN_NF64 * sizeof(double), cudaMemcpyDeviceToHost));
-      else {
-        e.resize(nb * R3D_BIN_NF64);
-        CK(cudaMemcpy(e.data(), D.M.energies, e.size() * sizeof(double), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < e.size(); i++) energies[i] += e[i];
+  for (DevState *D : h->devs) {
+    if (int rc = drain(*D)) return rc;
+    CK(cudaSetDevice(D->device));
+    CK(cudaStreamSynchronize(D->stream));
+  }
+  if (h->devs.size() > 1 && h->peer_ok) {
+    // the sum over devices, on device slot 0 over peer memory; then ONE device-to-host copy of each array
+    DevState &D0 = *h->devs[0];
+    CK(cudaSetDevice(D0.device));
+    PeerPtrs pf, pi;
+    pf.n = pi.n = (int)h->devs.size();
+    for (int g = 0; g < pf.n; g++) { pf.p[g] = h->devs[g]->M.energies; pi.p[g] = h->devs[g]->ibuf; }
+    const size_t or_index = D0.n_ibuf - R3D_NDIAG_LANES - R3D_NCOUNTERS + R3D_CNT_DIAG;
+    if (energies && nb) combine_f64_kernel<<<296, 256, 0, D0.stream>>>(pf, D0.n_fbuf, h->sum_f64);
+    combine_u64_kernel<<<296, 256, 0, D0.stream>>>(pi, D0.n_ibuf, or_index, h->sum_i64);
+    D0.launches += (energies && nb) ? 2 : 1;
+    CK(cudaGetLastError());
+    if (energies && nb) CK(cudaMemcpyAsync(energies, h->sum_f64, nb * R3D_BIN_NF64 * sizeof(double), cudaMemcpyDeviceToHost, D0.stream));
+    if (counts && nb) CK(cudaMemcpyAsync(counts, h->sum_i64, nb * R3D_BIN_NCNT * sizeof(uint64_t), cudaMemcpyDeviceToHost, D0.stream));
+    CK(cudaMemcpyAsync(ksum, h->sum_i64 + (D0.n_ibuf - R3D_NDIAG_LANES - R3D_NCOUNTERS), sizeof ksum, cudaMemcpyDeviceToHost, D0.stream));
+    CK(cudaStreamSynchronize(D0.stream));
+  } else {
+    // one device (or devices that are not peers: summed on the host, device by device)
+    std::vector<double> e;
+    std::vector<unsigned long long> c;
+    for (size_t g = 0; g < h->devs.size(); g++) {
+      DevState &D = *h->devs[g];
+      CK(cudaSetDevice(D.device));
+      if (energies && nb) {
+        if (g == 0) CK(cudaMemcpyAsync(energies, D.M.energies, nb * R3D_BIN_NF64 * sizeof(double), cudaMemcpyDeviceToHost, D.stream));
+        else {
+          e.resize(nb * R3D_BIN_NF64);
+          CK(cudaMemcpy(e.data(), D.M.energies, e.size() * sizeof(double), cudaMemcpyDeviceToHost));
+          for (size_t i = 0; i < e.size(); i++) energies[i] += e[i];
+        }
       }
-    }
-    if (counts && nb) {
-      if (g == 0) CK(cudaMemcpy(counts, D.M.counts, nb * R3D_BIN_NCNT * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-      else {
-        c.resize(nb * R3D_BIN_NCNT);
-        CK(cudaMemcpy(c.data(), D.M.counts, c.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < c.size(); i++) counts[i] += c[i];
+      if (counts && nb) {
+        if (g == 0) CK(cudaMemcpyAsync(counts, D.M.counts, nb * R3D_BIN_NCNT * sizeof(uint64_t), cudaMemcpyDeviceToHost, D.stream));
+        else {
+          c.resize(nb * R3D_BIN_NCNT);
+          CK(cudaMemcpy(c.data(), D.M.counts, c.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+          for (size_t i = 0; i < c.size(); i++) counts[i] += c[i];
+        }
       }
+      CK(cudaMemcpyAsync(k, D.M.counters, sizeof k, cudaMemcpyDeviceToHost, D.stream));
+      CK(cudaStreamSynchronize(D.stream));
+      for (int i = 0; i < R3D_NCOUNTERS; i++) { if (i == R3D_CNT_DIAG) ksum[i] |= k[i]; else ksum[i] += k[i]; }
     }
-    CK(cudaMemcpy(k, D.M.counters, sizeof k, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < R3D_NCOUNTERS; i++) { if (i == R3D_CNT_DIAG) ksum[i] |= k[i]; else ksum[i] += k[i]; }
   }
   if (counters) for (int i = 0; i < R3D_NCOUNTERS; i++) counters[i] = ksum[i];
   if (diag) *diag = (uint32_t)ksum[R3D_CNT_DIAG];
@@ -766,14 +892,12 @@ int r3d_fetch(r3d_handle *h, double *energies, uint64_t *counts, uint64_t *count
 int r3d_reset(r3d_handle *h) {
   DeviceGuard guard;
   if (!h) return fail(R3D_EINVAL, "null handle");
-  const size_t nb = std::max<size_t>((size_t)h->n_seis * h->n_bins, 1);
   for (DevState *Dp : h->devs) {
     DevState &D = *Dp;
     if (int rc = drain(D)) return rc;
     CK(cudaSetDevice(D.device));
-    CK(cudaMemsetAsync(D.M.energies, 0, nb * R3D_BIN_NF64 * sizeof(double), D.stream));
-    CK(cudaMemsetAsync(D.M.counts, 0, nb * R3D_BIN_NCNT * sizeof(unsigned long long), D.stream));
-    CK(cudaMemsetAsync(D.M.counters, 0, R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
+    CK(cudaMemsetAsync(D.M.energies, 0, D.n_fbuf * sizeof(double), D.stream));
+    CK(cudaMemsetAsync(D.ibuf, 0, D.n_ibuf * sizeof(unsigned long long), D.stream));
     CK(cudaMemsetAsync(D.block_tally, 0, (size_t)D.grid * R3D_NCOUNTERS * sizeof(unsigned long long), D.stream));
     CK(cudaStreamSynchronize(D.stream));
   }
@@ -785,6 +909,18 @@ int r3d_device_accumulators(r3d_handle *h, int dev_slot, void **energies, void *
   if (energies) *energies = h->devs[dev_slot]->M.energies;
   if (counts) *counts = h->devs[dev_slot]->M.counts;
   if (counters) *counters = h->devs[dev_slot]->M.counters;
+  return 0;
+}
+
+int r3d_device_accumulator_blocks(r3d_handle *h, int dev_slot, void **f64_block, uint64_t *n_f64, void **i64_block,
+                                  uint64_t *n_i64, uint64_t *counters_at) {
+  if (!h || dev_slot < 0 || dev_slot >= (int)h->devs.size()) return fail(R3D_EINVAL, "bad handle or device slot");
+  DevState &D = *h->devs[dev_slot];
+  if (f64_block) *f64_block = D.M.energies;
+  if (n_f64) *n_f64 = D.n_fbuf;
+  if (i64_block) *i64_block = D.ibuf;
+  if (n_i64) *n_i64 = D.n_ibuf;
+  if (counters_at) *counters_at = D.n_ibuf - R3D_NDIAG_LANES - R3D_NCOUNTERS;
   return 0;
 }
 

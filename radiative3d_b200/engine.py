@@ -20,7 +20,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libr3dgpu.
 _lib = None
 
 EXPORTS = [
-    "r3d_create", "r3d_run", "r3d_sync", "r3d_fetch", "r3d_reset", "r3d_device_accumulators", "r3d_stream",
+    "r3d_create", "r3d_run", "r3d_sync", "r3d_fetch", "r3d_reset", "r3d_device_accumulators", "r3d_device_accumulator_blocks", "r3d_stream",
     "r3d_launch_count", "r3d_trace", "r3d_trace_events", "r3d_build_scatterer_tables", "r3d_toa_create", "r3d_scatterer_g_values", "r3d_toa_destroy", "r3d_set_profiling", "r3d_kernel_times", "r3d_test_cdf_search", "r3d_test_path_to_boundary", "r3d_test_advance",
     "r3d_test_transform", "r3d_test_rtcoef", "r3d_test_catch", "r3d_destroy", "r3d_last_error", "r3d_abi_version",
 ]
@@ -52,6 +52,7 @@ def load_library(path=None):
     L.r3d_fetch.argtypes = [vp, pd, pu64, pu64, pu32]
     L.r3d_reset.argtypes = [vp]
     L.r3d_device_accumulators.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.r3d_device_accumulator_blocks.argtypes = [vp, C.c_int, C.POINTER(vp), pu64, C.POINTER(vp), pu64, pu64]
     L.r3d_stream.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.r3d_launch_count.argtypes = [vp, pu64]
     L.r3d_trace.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
@@ -97,12 +98,19 @@ class _CudaView:
 class Engine:
     """The GPU propagate path for one flattened model, replicated on `devices`."""
 
-    def __init__(self, model: FlatModel, devices=(0,)):
+    def __init__(self, model: FlatModel, devices=(0,), device_tables=None):
+        """device_tables: {name: device pointer or (device pointer, owner)} for any of the five large tables
+        (distributed.BIG_TABLES) that are already in device memory - e.g. received by distributed.broadcast_model_tables -
+        and must be complete (synchronise the producing stream first); the model's host arrays still give the shapes."""
         self._L = load_library()
         self.model = model
         self.devices = tuple(devices)
         self._h = C.c_void_p()
         d = model.desc()
+        for name, ptr in (device_tables or {}).items():
+            if name not in ("toa_theta", "toa_phi", "src_cdf", "scat_cdf", "scat_spol"):
+                raise ValueError(f"{name} cannot be given in device memory (include/r3d_gpu.h)")
+            setattr(d, name, C.cast(C.c_void_p(ptr[0] if isinstance(ptr, tuple) else ptr), C.POINTER(C.c_double)))
         dev = (C.c_int * len(self.devices))(*self.devices)
         _ck(self._L, self._L.r3d_create(C.byref(d), dev, len(self.devices), C.byref(self._h)))
 
@@ -208,6 +216,14 @@ class Engine:
         return (_CudaView(e.value, (nb * abi.R3D_BIN_NF64,), "<f8", self),
                 _CudaView(c.value, (nb * abi.R3D_BIN_NCNT,), "<i8", self),
                 _CudaView(k.value, (abi.R3D_NCOUNTERS,), "<i8", self))
+
+    def device_accumulator_blocks(self, slot=0):
+        """The same accumulators as two device-resident blocks for in-place collectives, one per element type:
+        (f64 block = energies, i64 block = counts | counters | diagnostic-bit lanes, index of the counters in the i64 block)."""
+        f, i = C.c_void_p(), C.c_void_p()
+        nf, ni, at = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _ck(self._L, self._L.r3d_device_accumulator_blocks(self._h, slot, C.byref(f), C.byref(nf), C.byref(i), C.byref(ni), C.byref(at)))
+        return (_CudaView(f.value, (nf.value,), "<f8", self), _CudaView(i.value, (ni.value,), "<i8", self), int(at.value))
 
     # -- deterministic sub-kernels (r3d_test_*) --
     def _rows(self, fn, win, wout, x):

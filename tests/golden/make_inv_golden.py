@@ -16,7 +16,9 @@ time_nan        halfspace   mVelTop[S]=NaN, S MFP 3 km        INV_TIME_NAN (no s
                                                               time to an unsigned bin index, dataout.cpp:163 - undefined behaviour)
 path_negative   halfspace   S MFP -3 km                       INV_PATH_NEGATIVE, and INV_TIME_NEGATIVE for phonons whose long P legs
                                                               keep the path length positive while the recent travel time is negative
-stuck           halfspace   S MFP 0                           INV_STUCK
+stuck           halfspace   S MFP 0, free surface absorbing   INV_STUCK (with the surface reflecting, P->SV conversions put S phonons ON the
+                                                              surface plane, where "0 < distance to the face" is decided by the last bit
+                                                              of the position: the outcome would hinge on FMA contraction, not on the check)
 slow            halfspace   S MFP 3 km, cm_slow_concern 1e4 s INV_SLOW
 loop_exceed     halfspace   S MFP 3 km, cm_loop_concern 200,  INV_LOOP_EXCEED
                             TTL 1e9 s
@@ -44,7 +46,7 @@ CASES = {
     "path_nan": ("spherical", 2, 400, "shell_zr2_p=nan", True, 0x01),
     "time_nan": ("halfspace", 2, 1500, "cyl_vel_s=nan,mfp_s=3", False, 0x02),
     "path_negative": ("halfspace", 2, 1500, "mfp_s=-3", True, 0x0c),
-    "stuck": ("halfspace", 2, 1500, "mfp_s=0", True, 0x10),
+    "stuck": ("halfspace", 2, 1500, "mfp_s=0,no_reflect=1", True, 0x10),
     "slow": ("halfspace", 2, 1500, "mfp_s=3,slow=1e4", True, 0x20),
     "loop_exceed": ("halfspace", 2, 1500, "mfp_s=3,loop=200,ttl=1e9", True, 0x40),
 }

@@ -37,8 +37,15 @@ WORKER = textwrap.dedent("""
     e, c, k, _ = ob.run(m, first, n, 77)
     if rank == 1:
         k[7] |= np.uint64(1 << 4)                 # pretend rank 1 saw a STUCK phonon: the OR must survive
+    # the same reduction on a handle's two accumulator blocks (include/r3d_gpu.h: r3d_device_accumulator_blocks), to rank 0
+    import torch
+    from radiative3d_b200 import abi
+    lanes = np.array([(int(k[7]) >> b) & 1 for b in range(abi.R3D_NDIAG_LANES)], dtype=np.int64)
+    fblk = torch.from_numpy(e.reshape(-1).copy())
+    iblk = torch.from_numpy(np.concatenate([c.reshape(-1).view(np.int64), k.view(np.int64), lanes]))
+    distributed.all_reduce_blocks(fblk, iblk, c.size, dst=0)
     distributed.all_reduce_numpy(e, c, k)
-    np.savez({out!r} + f".{{rank}}.npz", e=e, c=c, k=k)
+    np.savez({out!r} + f".{{rank}}.npz", e=e, c=c, k=k, fblk=fblk.numpy(), iblk=iblk.numpy())
     dist.destroy_process_group()
 """)
 
@@ -65,3 +72,9 @@ def test_two_ranks_match_single_process(tmp_path):
         assert int(z["k"][7]) == 1 << 4
         assert np.abs(z["e"] - e).max() <= 1e-12 * max(1.0, np.abs(e).max())
     assert c.sum() > 0
+    # two collectives on the blocks, reduced to rank 0: same numbers, diagnostic word rebuilt from its lanes
+    z = np.load(out + ".0.npz")
+    assert np.array_equal(z["iblk"][:c.size].view(np.uint64), c.reshape(-1))
+    assert np.array_equal(z["iblk"][c.size:c.size + 7].view(np.uint64), k[:7])
+    assert int(z["iblk"][c.size + 7]) == 1 << 4
+    assert np.abs(z["fblk"] - e.reshape(-1)).max() <= 1e-12 * max(1.0, np.abs(e).max())
