@@ -749,6 +749,7 @@ int r3d_create(const r3d_model_desc *desc, const int *devices, int n_dev, r3d_ha
   // and guides.  Peer access in both directions between slot 0 and every other slot also serves r3d_fetch's sum.
   r3d_model_desc from0 = *desc;
   bool peers = n_dev > 1 && n_dev <= R3D_MAX_PEERS && env_int("R3D_PEER_COMBINE", 1) != 0;
+  const bool replicate = n_dev > 1 && env_int("R3D_PEER_REPLICATE", 1) != 0;
   for (int i = 0; i < n_dev; i++) {
     int dev = devices ? devices[i] : i;
     if (dev < 0 || dev >= count) { r3d_destroy(h); return fail(R3D_ENODEV, "device index out of range"); }
@@ -756,28 +757,31 @@ int r3d_create(const r3d_model_desc *desc, const int *devices, int n_dev, r3d_ha
     DevState *D = new DevState();
     h->devs.push_back(D);
     D->device = dev;
-    if (int rc = build_device(*D, i == 0 ? desc : &from0)) return bail(rc);
-    if (i == 0 && n_dev > 1 && env_int("R3D_PEER_REPLICATE", 1) != 0) {
-      from0.toa_theta = D->raw_theta; from0.toa_phi = D->raw_phi; from0.src_cdf = D->M.src_cdf;
-      from0.scat_cdf = D->M.scat_cdf; from0.scat_spol = D->raw_spol;
-    }
-    if (i > 0 && peers) {
+    bool linked = false;                      // this device and slot 0 can read each other's pool memory
+    if (i > 0 && (peers || replicate)) {
       const int d0 = h->devs[0]->device;
       int a = 0, b = 0;
-      if (cudaDeviceCanAccessPeer(&a, d0, dev) != cudaSuccess || cudaDeviceCanAccessPeer(&b, dev, d0) != cudaSuccess || !a || !b) peers = false;
-      else {
+      if (cudaDeviceCanAccessPeer(&a, d0, dev) == cudaSuccess && cudaDeviceCanAccessPeer(&b, dev, d0) == cudaSuccess && a && b) {
         cudaMemPool_t p0, pi;
         if (int rc = device_pool(d0, &p0)) return bail(rc);
         if (int rc = device_pool(dev, &pi)) return bail(rc);
         cudaMemAccessDesc acc;
+        memset(&acc, 0, sizeof acc);
         acc.flags = cudaMemAccessFlagsProtReadWrite;
         acc.location.type = cudaMemLocationTypeDevice;
         acc.location.id = d0;
-        if (cudaMemPoolSetAccess(pi, &acc, 1) != cudaSuccess) peers = false;       // slot 0 reads this device's accumulators
+        const bool ok1 = cudaMemPoolSetAccess(pi, &acc, 1) == cudaSuccess;      // slot 0 reads this device's accumulators
         acc.location.id = dev;
-        if (cudaMemPoolSetAccess(p0, &acc, 1) != cudaSuccess) peers = false;       // (and this device may read slot 0's tables)
-        cudaGetLastError();
+        const bool ok2 = cudaMemPoolSetAccess(p0, &acc, 1) == cudaSuccess;      // this device reads slot 0's tables
+        linked = ok1 && ok2;
       }
+      cudaGetLastError();
+      if (!linked) peers = false;
+    }
+    if (int rc = build_device(*D, (i > 0 && linked && replicate) ? &from0 : desc)) return bail(rc);
+    if (i == 0 && replicate) {
+      from0.toa_theta = D->raw_theta; from0.toa_phi = D->raw_phi; from0.src_cdf = D->M.src_cdf;
+      from0.scat_cdf = D->M.scat_cdf; from0.scat_spol = D->raw_spol;
     }
     D->worker = std::thread(worker_main, D);
   }
