@@ -355,6 +355,11 @@ int r3d_test_transform(const double *in, uint32_t n, double *out);
  * choice, dirx,diry,dirz, pdx,pdy,pdz}. */
 int r3d_test_rtcoef(const double *in, uint32_t n, double *out);
 
+/* The straight-line division and square root of the hot paths (r3d_device.cuh: qdiv, qsqrt0) next to the compiler's own:
+ * in[i] = {a, b}; out[i] = {qdiv(a, b), a / b, qsqrt0(a), sqrt(a)}.  The pairs must agree bit for bit over the operand
+ * range of a phonon event. */
+int r3d_test_arith(const double *in, uint32_t n, double *out);
+
 /* Seismometer::CatchPhonon (dataout.cpp:103-216) for one seismometer record:
  * in[i] = {seis[18], time, x,y,z, theta,phi,pol, type, amp, vel};
  * out[i] = {caught(0/1), bin, ex,ey,ez, e}. */

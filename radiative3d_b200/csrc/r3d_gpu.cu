@@ -216,6 +216,12 @@ __global__ void test_rtcoef_kernel(const double *in, uint32_t n, double *out) {
   for (int k = 0; k < 6; k++) o[k] = rt.prob[k];
   o[6] = rt.choice; o[7] = od.x; o[8] = od.y; o[9] = od.z; o[10] = pd.x; o[11] = pd.y; o[12] = pd.z;
 }
+__global__ void test_arith_kernel(const double *in, uint32_t n, double *out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = in[2 * i], b = in[2 * i + 1];
+  out[4 * i] = qdiv(a, b); out[4 * i + 1] = a / b; out[4 * i + 2] = qsqrt0(a); out[4 * i + 3] = sqrt(a);
+}
 __global__ void test_catch_kernel(double bin_dt, uint32_t n_bins, const double *in, uint32_t n, double *out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -264,7 +270,9 @@ struct DevState {
   unsigned long long launches = 0;
   double k_seconds = 0;                    // device time of the propagate kernel alone since r3d_set_profiling
   unsigned long long k_launches = 0;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};    // job begin / end, kernel begin / end (made once per device)
+  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};    // job begin / end, kernel begin / end, 3 for the pilot launches (made once per device)
+  int wide = -1;                           // layered models: 1 = the 512-thread variant of the kernel, 0 = the 384-thread one, -1 = not decided yet
+  int wide_threads = 0;
   // the integer accumulators are one allocation, so that a launcher can all-reduce them with ONE collective:
   // counts [n_seis*n_bins*2] | counters [R3D_NCOUNTERS] | diag lanes [R3D_NDIAG_LANES] (lane b = 1 if bit b of the diagnostic
   // word is set: lanes survive a SUM all-reduce, the OR-combined word does not)
@@ -338,9 +346,9 @@ propagate_fn pick_propagate_of(bool trace, bool small) {
   if (small) return trace ? propagate_kernel<Cell, true, true> : propagate_kernel<Cell, false, true>;
   return trace ? propagate_kernel<Cell, true, false> : propagate_kernel<Cell, false, false>;
 }
-propagate_fn pick_propagate(uint32_t kind, bool trace, bool small) {
+propagate_fn pick_propagate(uint32_t kind, bool trace, bool small, bool wide = false) {
   switch (kind) {
-    case R3D_CELL_CYLINDER: return pick_propagate_of<Cylinder>(trace, small);
+    case R3D_CELL_CYLINDER: return wide ? pick_propagate_of<CylinderWide>(trace, small) : pick_propagate_of<Cylinder>(trace, small);
     case R3D_CELL_SHELL: return pick_propagate_of<Shell>(trace, small);
     default: return pick_propagate_of<Tetra>(trace, small);
   }
@@ -447,7 +455,7 @@ int env_int(const char *name, int dflt) {
 int build_device(DevState &D, const r3d_model_desc *d) {
   CK(cudaSetDevice(D.device));
   CK(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 4; i++) CK(cudaEventCreate(&D.ev[i]));
+  for (int i = 0; i < 7; i++) CK(cudaEventCreate(&D.ev[i]));
   const bool timing = env_int("R3D_TIMING", 0) != 0;
   auto t_start = std::chrono::steady_clock::now();
   auto lap = [&](const char *what) {
@@ -494,7 +502,35 @@ int build_device(DevState &D, const r3d_model_desc *d) {
     D.raw_spol = spol_raw;
   }
   lap("cdf tables, spol");
-  if (int rc = dev_upload(D, &M.cell_params, d->cell_params, nc * d->cell_nparam)) return rc;
+  {
+    // The device's cell records are the caller's, followed by a few derived constants per cell (Cell::extra doubles): reciprocals
+    // and products that the reference re-derives with a division in every event (1 / v, pi f / Q, |grad v|).  Computed here
+    // in plain IEEE double arithmetic; the events multiply where the reference divides (within 2 ulp of it).
+    const uint32_t np = d->cell_nparam;
+    const uint32_t extra = (d->cell_kind == R3D_CELL_CYLINDER) ? Cylinder::extra : (d->cell_kind == R3D_CELL_SHELL) ? Shell::extra : Tetra::extra;
+    std::vector<double> rec((size_t)nc * (np + extra));
+    for (size_t i = 0; i < nc; i++) {
+      const double *c = d->cell_params + i * np;
+      double *o = rec.data() + i * (np + extra);
+      memcpy(o, c, np * sizeof(double));
+      double *x = o + np;
+      const double pif = kPi * d->freq_hz;
+      if (d->cell_kind == R3D_CELL_CYLINDER) {
+        x[0] = 1.0 / c[0]; x[1] = 1.0 / c[1]; x[2] = pif / c[3]; x[3] = pif / c[4];
+      } else if (d->cell_kind == R3D_CELL_SHELL) {
+        x[0] = pif / c[8]; x[1] = pif / c[9];
+      } else {
+        x[0] = pif / c[12]; x[1] = pif / c[13];
+        for (int t = 0; t < 2; t++) {
+          const double g = sqrt(c[3 * t] * c[3 * t] + c[3 * t + 1] * c[3 * t + 1] + c[3 * t + 2] * c[3 * t + 2]);
+          x[2 + t] = g; x[4 + t] = 1.0 / g;
+        }
+      }
+    }
+    M.cell_nparam = np + extra;
+    if (int rc = dev_upload(D, &M.cell_params, rec.data(), rec.size())) return rc;
+    CK(cudaStreamSynchronize(D.stream));                      // (rec goes out of scope)
+  }
   if (int rc = dev_upload(D, &M.cell_scat, d->cell_scat, nc)) return rc;
   {
     // Layered (cylinder) cells have one velocity per wave type, so whether a neighbour face bends the ray or hands it
@@ -590,8 +626,8 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   // 1280 slots with 60 KB 1.99e9).  The carve-out steps are 132 / 164 / 196 / 228 KB.
   const size_t smem_cap = (size_t)std::max(16, env_int("R3D_SMEM_KB", 196)) * 1024 / D.blocks_per_sm - (size_t)prop.reservedSharedMemPerBlock - fattr.sharedSizeBytes;
   D.smem_block = std::min(D.smem_block, smem_cap / 16 * 16);
-  const uint32_t tb = Tab<true>::bytes(d->n_cells, d->cell_nparam, d->faces_per_cell, d->n_scat);
-  D.table_bytes = ((size_t)nc * d->cell_nparam * 8 + (size_t)ns * 80 <= (size_t)env_int("R3D_SMALL_TABLE_BYTES", 24 * 1024)) ? tb : 0u;
+  const uint32_t tb = Tab<true>::bytes(d->n_cells, M.cell_nparam, d->faces_per_cell, d->n_scat);
+  D.table_bytes = ((size_t)nc * M.cell_nparam * 8 + (size_t)ns * 80 <= (size_t)env_int("R3D_SMALL_TABLE_BYTES", 24 * 1024)) ? tb : 0u;
   const size_t for_slots = D.smem_block - D.table_bytes;
   D.max_slots[0] = (uint32_t)std::min<size_t>(for_slots / R3D_SLOT_BYTES / 32 * 32, 65504);
   D.max_slots[1] = (uint32_t)std::min<size_t>(for_slots / R3D_SLOT_BYTES_TRACE / 32 * 32, 65504);
@@ -600,7 +636,11 @@ int build_device(DevState &D, const r3d_model_desc *d) {
   }
   if (D.max_slots[1] < 32) return fail(R3D_EUNSUPPORTED, "shared memory too small for the phonon slots");
   for (int trace = 0; trace < 2; trace++)
-    CK(cudaFuncSetAttribute(pick_propagate(d->cell_kind, trace != 0, D.table_bytes != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_block));
+    for (int wide = 0; wide < (d->cell_kind == R3D_CELL_CYLINDER ? 2 : 1); wide++)
+      CK(cudaFuncSetAttribute(pick_propagate(d->cell_kind, trace != 0, D.table_bytes != 0, wide != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_block));
+  D.wide_threads = std::min((int)CylinderWide::threads, std::max(32, env_int("R3D_THREADS", CylinderWide::threads) / 32 * 32));
+  D.wide = (d->cell_kind == R3D_CELL_CYLINDER) ? env_int("R3D_CYL_WIDE", -1) : 0;      // (-1: decided by the first large job, run_job)
+  if (D.wide > 1) D.wide = 1;
   D.grid = prop.multiProcessorCount * D.blocks_per_sm;
   if (int rc = dev_alloc(D, &D.block_tally, (size_t)D.grid * R3D_NCOUNTERS)) return rc;
   if (int rc = dev_alloc(D, &D.block_clock, (size_t)D.grid * R3D_NCLOCKS)) return rc;
@@ -617,15 +657,19 @@ int build_device(DevState &D, const r3d_model_desc *d) {
 // job of more than kMaxPerLaunch phonons: a slot keeps its phonon's index relative to the launch's first phonon in 32 bits,
 // and the per-thread tallies are 32-bit (a thread sees phonons / (CTAs x threads) of a launch, so 2^30 phonons per launch
 // leave room for 2 x 10^5 loop events per phonon on average).
+// Layered models have two builds of the kernel (Cylinder, CylinderWide: r3d_device.cuh).  The first job of at least
+// kPilotMin phonons starts with two pilot launches of kPilot phonons each, one per build, timed with CUDA events; the
+// faster build then runs the rest of the job and everything after it on this handle.  The pilots are part of the job (their
+// phonons are traced once, like all others; results do not depend on the build), so the choice costs no extra work.
 constexpr unsigned long long kMaxPerLaunch = 1ull << 30;
+constexpr unsigned long long kPilot = 2000000ull, kPilotMin = 16000000ull;
 int run_job(DevState &D, const JobReq &jr) {
   CK(cudaSetDevice(D.device));
   cudaEvent_t ev0 = D.ev[0], ev1 = D.ev[1], ek0 = D.ev[2], ek1 = D.ev[3];
   CK(cudaEventRecord(ev0, D.stream));
   const bool trace = jr.finals != nullptr || jr.events != nullptr;
   unsigned long long n_launch = 0;
-  for (unsigned long long done = 0; done < jr.n;) {
-    const unsigned long long n = std::min(jr.n - done, kMaxPerLaunch);
+  auto launch = [&](unsigned long long done, unsigned long long n, bool wide) -> int {
     Job J; J.first = jr.first + done; J.n = n; J.seed = jr.seed; J.finals = jr.finals ? jr.finals + done : nullptr;
     J.events = jr.events; J.event_cursor = jr.event_cursor; J.event_cap = jr.event_cap; J.event_mask = jr.event_mask;
     // no more slots than phonons: a small job is spread over all CTAs instead of filling the first few
@@ -637,9 +681,30 @@ int run_job(DevState &D, const JobReq &jr) {
     const int grid = (int)std::min<unsigned long long>((unsigned long long)D.grid, need);
     CK(cudaMemsetAsync(D.M.next_phonon, 0, sizeof(unsigned long long), D.stream));
     if (!n_launch) CK(cudaEventRecord(ek0, D.stream));
-    pick_propagate(D.cell_kind, trace, D.table_bytes != 0)<<<grid, D.threads, smem, D.stream>>>(D.M, J, S, D.table_bytes, D.block_tally, D.block_clock);
+    pick_propagate(D.cell_kind, trace, D.table_bytes != 0, wide)<<<grid, wide ? D.wide_threads : D.threads, smem, D.stream>>>(D.M, J, S, D.table_bytes, D.block_tally, D.block_clock);
     D.launches += 1;
     n_launch++;
+    return 0;
+  };
+  unsigned long long done = 0;
+  if (D.wide < 0 && !trace && jr.n >= kPilotMin) {
+    CK(cudaEventRecord(D.ev[4], D.stream));
+    if (int rc = launch(0, kPilot, false)) return rc;
+    CK(cudaEventRecord(D.ev[5], D.stream));
+    if (int rc = launch(kPilot, kPilot, true)) return rc;
+    CK(cudaEventRecord(D.ev[6], D.stream));
+    CK(cudaEventSynchronize(D.ev[6]));
+    float narrow_ms = 0, wide_ms = 0;
+    CK(cudaEventElapsedTime(&narrow_ms, D.ev[4], D.ev[5]));
+    CK(cudaEventElapsedTime(&wide_ms, D.ev[5], D.ev[6]));
+    D.wide = wide_ms < narrow_ms ? 1 : 0;
+    if (env_int("R3D_TIMING", 0)) fprintf(stderr, "r3d_run: pilot launches of %llu phonons: 384 threads %.3f ms, 512 threads %.3f ms\n", kPilot, narrow_ms, wide_ms);
+    done = 2 * kPilot;
+  }
+  const bool wide = D.wide > 0;
+  while (done < jr.n) {
+    const unsigned long long n = std::min(jr.n - done, kMaxPerLaunch);
+    if (int rc = launch(done, n, wide)) return rc;
     done += n;
   }
   if (n_launch) CK(cudaEventRecord(ek1, D.stream));
@@ -715,7 +780,7 @@ void destroy_device(DevState *D) {
     if (D->stream) cudaStreamSynchronize(D->stream);
     for (void *p : D->allocs) cudaFreeAsync(p, D->stream);
     if (D->stream) cudaStreamSynchronize(D->stream);
-    for (int i = 0; i < 4; i++) if (D->ev[i]) cudaEventDestroy(D->ev[i]);
+    for (int i = 0; i < 7; i++) if (D->ev[i]) cudaEventDestroy(D->ev[i]);
     if (D->stream) cudaStreamDestroy(D->stream);
   }
   delete D;
@@ -972,7 +1037,7 @@ int r3d_kernel_times(r3d_handle *h, double seconds[3], uint64_t launches[3], uin
   if (env_int("R3D_TIMING", 0)) {          // warp-cycles by kind of chunk, summed over CTAs
     unsigned long long k[R3D_NCLOCKS] = {0};
     for (int b = 0; b < D.grid; b++) for (int i = 0; i < R3D_NCLOCKS; i++) k[i] += clk[R3D_NCLOCKS * b + i];
-    const char *nm[4] = {"advance", "refill", "face", "draw"};
+    const char *nm[4] = {"advance", "bend", "face", "draw"};
     double tot = (double)k[11];
     for (int i = 0; i < 4; i++) tot += (double)k[3 + i];
     for (int i = 0; i < 4; i++)
@@ -1215,6 +1280,9 @@ int r3d_test_transform(const double *in, uint32_t n, double *out) {
 }
 int r3d_test_rtcoef(const double *in, uint32_t n, double *out) {
   return rows_hook([&](double *a, double *b) { test_rtcoef_kernel<<<(n + 127) / 128, 128>>>(a, n, b); }, in, n, 15, 13, out);
+}
+int r3d_test_arith(const double *in, uint32_t n, double *out) {
+  return rows_hook([&](double *a, double *b) { test_arith_kernel<<<(n + 127) / 128, 128>>>(a, n, b); }, in, n, 2, 4, out);
 }
 int r3d_test_catch(double bin_dt, uint32_t n_bins, const double *in, uint32_t n, double *out) {
   return rows_hook([&](double *a, double *b) { test_catch_kernel<<<(n + 127) / 128, 128>>>(bin_dt, n_bins, a, n, b); }, in, n, 28, 6, out);

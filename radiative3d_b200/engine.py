@@ -22,7 +22,7 @@ _lib = None
 EXPORTS = [
     "r3d_create", "r3d_run", "r3d_sync", "r3d_fetch", "r3d_reset", "r3d_device_accumulators", "r3d_device_accumulator_blocks", "r3d_stream",
     "r3d_launch_count", "r3d_trace", "r3d_trace_events", "r3d_build_scatterer_tables", "r3d_toa_create", "r3d_scatterer_g_values", "r3d_toa_destroy", "r3d_set_profiling", "r3d_kernel_times", "r3d_test_cdf_search", "r3d_test_path_to_boundary", "r3d_test_advance",
-    "r3d_test_transform", "r3d_test_rtcoef", "r3d_test_catch", "r3d_destroy", "r3d_last_error", "r3d_abi_version",
+    "r3d_test_transform", "r3d_test_rtcoef", "r3d_test_catch", "r3d_test_arith", "r3d_destroy", "r3d_last_error", "r3d_abi_version",
 ]
 
 
@@ -65,6 +65,7 @@ def load_library(path=None):
     L.r3d_test_advance.argtypes = [vp, pd, C.c_uint32, pd]
     L.r3d_test_transform.argtypes = [pd, C.c_uint32, pd]
     L.r3d_test_rtcoef.argtypes = [pd, C.c_uint32, pd]
+    L.r3d_test_arith.argtypes = [pd, C.c_uint32, pd]
     L.r3d_test_catch.argtypes = [C.c_double, C.c_uint32, pd, C.c_uint32, pd]
     L.r3d_destroy.argtypes = [vp]
     L.r3d_destroy.restype = None
@@ -282,6 +283,11 @@ def transform(x):
 
 def rtcoef(x):
     return _free_rows("r3d_test_rtcoef", 15, 13, x)
+
+
+def arith(x):
+    """rows {a, b} -> {qdiv(a, b), a / b, qsqrt0(a), sqrt(a)} on the device (r3d_device.cuh)."""
+    return _free_rows("r3d_test_arith", 2, 4, x)
 
 
 def catch(bin_dt, n_bins, x):

@@ -154,3 +154,25 @@ def test_catch(cfg):
     assert np.array_equal(out[:, :2], ref[:, :2])
     assert np.array_equal(out[:, :2], z["catch_out"][:, :2])
     assert rel_err(out[:, 2:], ref[:, 2:]).max() <= TOL
+
+
+def test_branch_free_arithmetic():
+    """qdiv / qsqrt0 (r3d_device.cuh) are the compiler's own fast paths without the range tests: bit-identical to a / b and
+    sqrt(a) over the operand range of a phonon event (and far beyond it), including zero numerators, zero radicands and NaN."""
+    rng = np.random.default_rng(7)
+    n = 2_000_000
+    a = rng.standard_normal(n) * 10.0 ** rng.uniform(-60, 60, n)
+    b = rng.standard_normal(n) * 10.0 ** rng.uniform(-60, 60, n)
+    a[:1000] = 0.0                                   # 0 / b
+    a[1000:2000] = rng.uniform(0, 1, 1000)           # direction cosines over lengths
+    b[1000:2000] = rng.uniform(1e-7, 1, 1000)
+    a[2000:2010] = np.nan
+    b[2010:2020] = np.nan
+    a[2020:3020] = -0.0
+    b[b == 0] = 1.0
+    out = engine.arith(np.stack([a, b], axis=1))
+    q, q_ref, r, r_ref = out[:, 0], out[:, 1], out[:, 2], out[:, 3]
+    same_q = (q.view(np.uint64) == q_ref.view(np.uint64)) | (np.isnan(q) & np.isnan(q_ref)) | ((q == 0) & (q_ref == 0))   # (+0 for -0: documented)
+    assert same_q.all(), f"{(~same_q).sum()} quotients differ, e.g. {a[~same_q][:3]} / {b[~same_q][:3]}"
+    same_r = (r.view(np.uint64) == r_ref.view(np.uint64)) | (np.isnan(r) & np.isnan(r_ref))
+    assert same_r.all(), f"{(~same_r).sum()} roots differ, e.g. {a[~same_r][:3]}"
