@@ -41,18 +41,20 @@ WORKLOAD = "halfspace_nearsrc50"          # BASELINE.json configs[1]: the config
 TOA_DEGREE = int(os.environ.get("R3D_BENCH_TOA_DEGREE", "9"))      # the scripted degree (do-fundamentals.sh:82); the override is for the test-suite
 SEED = 20261018
 # The five BASELINE.json configs (radiative3d_b200/workloads.py holds their command lines).  per_gpu = phonons per GPU per
-# step, sized so that a step is 50-150 ms of device time; ref_per_proc / ref_one_core = the bounded samples of the CPU arms
+# step, sized so that a step is 50-350 ms of device time and at least ~150 phonons pass through every slot of the kernel (a
+# step is one launch: its ramp-up and its tail - the last, longest-lived phonons - cost about as much as ~20 phonons per
+# slot, which a production run of 1e9 phonons does not notice); ref_per_proc / ref_one_core = the bounded samples of the CPU arms
 # (the reference does 2e5 / 6e3 / 3e3 / 3e2 phonons per second and core on halfspace / crust pinch / Lop Nor / whole-Earth).
 WORKLOADS = {
     "halfspace": dict(script="do-halfspace.sh", per_gpu=125_000_000, ref_per_proc=400_000, ref_one_core=1_500_000,
                       what="Halfspace model, 144 seismometers x 400 bins"),
     "halfspace_nearsrc50": dict(script="do-halfspace-nearsrc50.sh", per_gpu=125_000_000, ref_per_proc=400_000, ref_one_core=1_500_000,
                                 what="Halfspace model, 144 seismometers x 1250 bins"),
-    "crustpinch": dict(script="do-crustpinch.sh", per_gpu=6_000_000, ref_per_proc=20_000, ref_one_core=60_000,
+    "crustpinch": dict(script="do-crustpinch.sh", per_gpu=30_000_000, ref_per_proc=20_000, ref_one_core=60_000,
                        what="crust-pinch model (2275 tetrahedra, interfaces with mode conversion), 480 seismometers x 300 bins"),
-    "lopnor": dict(script="do-lopnor.sh", per_gpu=8_000_000, ref_per_proc=10_000, ref_one_core=30_000,
+    "lopnor": dict(script="do-lopnor.sh", per_gpu=40_000_000, ref_per_proc=10_000, ref_one_core=30_000,
                    what="Lop Nor model (21 tilted layers, heterogeneous scattering), 320 seismometers x 300 bins"),
-    "spherical": dict(script="do-spherical.sh", per_gpu=1_000_000, ref_per_proc=1_000, ref_one_core=3_000,
+    "spherical": dict(script="do-spherical.sh", per_gpu=4_000_000, ref_per_proc=1_000, ref_one_core=3_000,
                       what="whole-Earth shells (quadratic-velocity layers), 480 seismometers x 400 bins"),
 }
 PER_GPU = WORKLOADS[WORKLOAD]["per_gpu"]

@@ -47,6 +47,7 @@
 #include <stdexcept>
 #include <ctime>
 #include <climits>
+#include <chrono>
 
 #define private public
 #define protected public
@@ -131,8 +132,13 @@ void ModelParams::OutputOctaveText(std::ostream * out) const {
 
 void Model::RunSimulation() {
 
+  typedef std::chrono::steady_clock Clock;
+  const Clock::time_point t_enter = Clock::now();
+  auto seconds_since = [](Clock::time_point t) { return std::chrono::duration<double>(Clock::now() - t).count(); };
+
   FlatModel F;
   Flatten(*this, F);
+  const double t_flatten = seconds_since(t_enter);
 
   if (const char * path = getenv("R3D_GPU_DUMP_MODEL")) {
     if (r3d_modelfile_write(path, &F.d) != 0) throw Runtime(std::string("cannot write model file ") + path);
@@ -148,7 +154,10 @@ void Model::RunSimulation() {
   if (opt.have_nph) nph = opt.nph;
 
   r3d_handle * h = 0;
+  const Clock::time_point t_c0 = Clock::now();
   r3d_check(r3d_create(&F.d, devices.data(), (int)devices.size(), &h), "r3d_create");
+  const double t_create = seconds_since(t_c0);
+  const Clock::time_point t_loop0 = Clock::now();
 
   std::cout << "@@ __BEGINNING_SIMULATION__" << std::endl << std::flush;
 
@@ -265,6 +274,8 @@ void Model::RunSimulation() {
   }
   if (!reporting) std::cerr << "100% of " << nph << " have been cast.\n";
   std::cout << "@@ __SIMULATION_COMPLETE__" << std::endl;
+  const double t_loop = seconds_since(t_loop0);
+  const Clock::time_point t_f0 = Clock::now();
 
   // bins and counters back into the reference's own objects
   std::vector<double> e(ns * nb * R3D_BIN_NF64 + 1);
@@ -303,6 +314,9 @@ void Model::RunSimulation() {
 
   std::cerr << "r3d-gpu: " << nph << " phonons on " << devices.size() << " device(s) in " << device_seconds
             << " s of device time (" << (device_seconds > 0 ? nph / device_seconds : 0) << " phonons/s), seed " << seed << "\n";
+  // host model in -> host bins out, as this program sees it (its model arrays are pageable std::vector memory)
+  std::cerr << "r3d-gpu: wall clock: flatten " << t_flatten << " s, r3d_create " << t_create << " s, loop " << t_loop
+            << " s, fetch + write-back " << seconds_since(t_f0) << " s; RunSimulation total " << seconds_since(t_enter) << " s\n";
 
   dataout.OutputPostSimSummary();
 

@@ -662,7 +662,7 @@ int build_device(DevState &D, const r3d_model_desc *d) {
 // faster build then runs the rest of the job and everything after it on this handle.  The pilots are part of the job (their
 // phonons are traced once, like all others; results do not depend on the build), so the choice costs no extra work.
 constexpr unsigned long long kMaxPerLaunch = 1ull << 30;
-constexpr unsigned long long kPilot = 2000000ull, kPilotMin = 16000000ull;
+constexpr unsigned long long kPilot = 2000000ull, kPilotMin = 8000000ull;
 int run_job(DevState &D, const JobReq &jr) {
   CK(cudaSetDevice(D.device));
   cudaEvent_t ev0 = D.ev[0], ev1 = D.ev[1], ek0 = D.ev[2], ek1 = D.ev[3];

@@ -397,21 +397,24 @@ R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
   bool dir_changed = false, s1_loaded = false;
   if (!fate) {
     const double *c = tab.cell(M, p.cell);
+    // The event's draws come first: path length, then at most two more, all from Philox block ordinal/4 (and the next one when
+    // they run over its end).  (The reference draws the path length after the distance to the boundary, phonons.cpp:590-601;
+    // taking it before keeps the generator's state and the logarithm out of the registers while the ray geometry - up to 20
+    // doubles of scratch for a curved ray - is live.  A phonon that times out on an infinite path has consumed no draw:
+    // `ordinal` only moves further down.)
+    Rng g; g.init(J.seed, J.first + A.idx(s));
+    const uint32_t o = ordinal & 3u, b = ordinal >> 2;
+    g.block(b);
+    const uint32_t w1 = g.w[1], w2 = g.w[2], w3 = g.w[3];
+    const uint32_t k_path = ((o == 0) ? g.w[0] : (o == 1) ? w1 : (o == 2) ? w2 : w3) >> 1;
+    const uint32_t scat = tab.scat(M, p.cell);
+    // Scatterer::GetRandomPathLength (scatterers.cpp:297-307)
+    const double r = 1.0 - ((double)k_path) * (1.0 / 2147483648.0);      // k / (RAND_MAX + 1): a power of two, exact either way
+    const double scatlen = -log(r) * tab.mfp(M, scat, p.type);
     typename Cell::Path P;
     const double edgelen = Cell::path(M, c, p.type, p.loc, p.dir, P);
     if (edgelen == pinf()) fate = R3D_FATE_TIMEOUT;             // phonons.cpp:595-598
     else {
-      // the event's draws: path length first, then at most two more, all from Philox block ordinal/4 (and the next
-      // one when they run over its end)
-      Rng g; g.init(J.seed, J.first + A.idx(s));
-      const uint32_t o = ordinal & 3u, b = ordinal >> 2;
-      g.block(b);
-      const uint32_t w1 = g.w[1], w2 = g.w[2], w3 = g.w[3];
-      const uint32_t k_path = ((o == 0) ? g.w[0] : (o == 1) ? w1 : (o == 2) ? w2 : w3) >> 1;
-      const uint32_t scat = tab.scat(M, p.cell);
-      // Scatterer::GetRandomPathLength (scatterers.cpp:297-307)
-      const double r = 1.0 - ((double)k_path) * (1.0 / 2147483648.0);      // k / (RAND_MAX + 1): a power of two, exact either way
-      const double scatlen = -log(r) * tab.mfp(M, scat, p.type);
       const bool scatter = scatlen < edgelen;
       const Travel tr = Cell::advance(M, c, p.type, scatter ? scatlen : edgelen, p.loc, p.dir, P);
       // Phonon::Move (phonons.cpp:62-70)
