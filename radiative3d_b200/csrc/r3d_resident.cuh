@@ -660,6 +660,80 @@ R3D_DEV void draw_batch(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
 }
 
 // =====================================================================================================
+// phase 2b, first half: DataReporter::ReportPhononCollected (dataout.cpp:545-568) + Seismometer::CatchPhonon (dataout.cpp:
+// 103-216) for the slots of one face chunk - as a WARP.  Every seismometer is pass-through (dataout.cpp:50), so all that
+// contain the arrival point must bin it; candidates come from the uniform grid over the seismometers' bounding spheres.
+// Few lanes of a chunk arrive at a collecting face, and each has a list of 10-20 candidates: lane by lane (even with the
+// lanes meeting at their n-th candidate) the scan ran at 1.4 of 32 lanes and the exact test at 1.3-2, 6.8 % of the warp
+// instructions and 10 % of the stall samples of the whole-Earth model.  Here the warp takes the arrivals one at a time
+// and spreads each one's candidates over its lanes: the arrival's state is read from its slot in shared memory by all
+// lanes (one broadcast read per field), 32 candidates get the sphere pre-test at once, and the lanes whose candidate passed
+// run the exact test and the bin update together.  The bins go straight to L2 as reductions (red.global.add.f64 / .u64:
+// 5.3e7 sectors in 124 ms on that model = 0.009 % of the L1-to-L2 write throughput, profiles/r2_histogram.md), so there is
+// nothing for an aggregation step in shared memory to win; catches per (seismometer, bin) are independent arrivals.
+// All 32 lanes call this; `have` = the lane holds a slot of the chunk.
+// =====================================================================================================
+template <class Cell, bool TRACE, class TabT>
+R3D_DEV void collect_warp(const DevModel &M, const Slots<TRACE> &A, const TabT &tab, bool have, uint32_t s, Tally &T) {
+  if (M.n_seis == 0) return;
+  const unsigned lane = threadIdx.x & 31u;
+  uint32_t i0 = 0, i1 = 0;
+  if (have) {
+    const uint4 meta = A.meta(s);
+    const uint2 q = A.req(s);
+    const int face = (int)((q.x >> 31) | ((q.y >> 31) << 1));
+    if (tab.flags(M, meta.y * M.faces_per_cell + face) & R3D_FACE_COLLECT) {
+      const double2 lxy = A.lxy(s);
+      const int cx_ = grid_axis_cell(lxy.x, M.grid_min[0], M.grid_inv_h[0]);
+      const int cy_ = grid_axis_cell(lxy.y, M.grid_min[1], M.grid_inv_h[1]);
+      const int cz_ = grid_axis_cell(A.lzdz(s).x, M.grid_min[2], M.grid_inv_h[2]);
+      if (cx_ >= 0 && cy_ >= 0 && cz_ >= 0 && cx_ < (int)M.grid_dim[0] && cy_ < (int)M.grid_dim[1] && cz_ < (int)M.grid_dim[2]) {
+        const uint32_t gcell = ((uint32_t)cz_ * M.grid_dim[1] + (uint32_t)cy_) * M.grid_dim[0] + (uint32_t)cx_;
+        i0 = __ldg(M.grid_start + gcell);
+        i1 = __ldg(M.grid_start + gcell + 1);
+      }
+    }
+  }
+  unsigned pending = __ballot_sync(R3D_FULL, i0 < i1);
+  while (pending) {
+    const int src = __ffs(pending) - 1;
+    pending &= pending - 1u;
+    const uint32_t ss = __shfl_sync(R3D_FULL, s, src), b0 = __shfl_sync(R3D_FULL, i0, src), b1 = __shfl_sync(R3D_FULL, i1, src);
+    // the arrival (same addresses in every lane: broadcast reads)
+    const double2 tp = A.tp(ss), ra = A.ra(ss), lxy = A.lxy(ss), lzdz = A.lzdz(ss), dxy = A.dxy(ss), sxy = A.sxy(ss);
+    const uint4 meta = A.meta(ss);
+    const v3 loc = V(lxy.x, lxy.y, lzdz.x), dir = V(dxy.x, dxy.y, lzdz.y);
+    const int type = (int)meta.w;
+    const v3 dopm = (type == R3D_RAY_P) ? dir : V(sxy.x, sxy.y, A.sz(ss));     // Phonon::DirectionOfMotion (phonons.cpp:201-211)
+    uint32_t caught = 0;
+    for (uint32_t base = b0; base < b1; base += 32u) {
+      const uint32_t j = base + lane;
+      if (j < b1) {
+        const uint32_t k2 = __ldg(M.grid_items + j);
+        const double2 qa = __ldg(reinterpret_cast<const double2 *>(M.seis_sphere + k2));
+        const double2 qb = __ldg(reinterpret_cast<const double2 *>(M.seis_sphere + k2) + 1);
+        const double ddx = qa.x - loc.x, ddy = qa.y - loc.y, ddz = qb.x - loc.z;
+        if (ddx * ddx + ddy * ddy + ddz * ddz <= qb.y) {            // may be within the gather radius: the exact CatchPhonon test
+          const double vel = Cell::veloc(tab.cell(M, meta.y), type, loc);
+          uint32_t bin; double e[4];
+          if (seis_catch(M.seis + (size_t)k2 * R3D_SEIS_NPARAM, M.bin_dt, M.n_bins, tp.x, loc, dir, dopm, type, exp(-ra.y), vel, bin, e)) {
+            const size_t bb = (size_t)k2 * M.n_bins + bin;
+            atomicAdd(M.energies + bb * 5 + 0, e[0]);
+            atomicAdd(M.energies + bb * 5 + 1, e[1]);
+            atomicAdd(M.energies + bb * 5 + 2, e[2]);
+            atomicAdd(M.energies + bb * 5 + 3 + type, e[3]);
+            atomicAdd(M.counts + bb * 2 + type, 1ull);
+            caught++;
+          }
+        }
+      }
+    }
+    T.v[R3D_CNT_CATCHES] += caught;                    // (a tally is summed over the threads at the end: whose it is does not matter)
+    if (TRACE && caught) atomicAdd(&A.tr(0, ss), caught);
+  }
+}
+
+// =====================================================================================================
 // phase 2b: everything that happens at a face that is not a plain hand-over: collection (dataout.cpp:545-568,
 // 103-216), free-surface / discontinuity R/T (phonons.cpp:429-476), Snell bending (phonons.cpp:311-405)
 // =====================================================================================================
@@ -680,53 +754,6 @@ R3D_DEV int face_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, con
   const uint32_t fl = tab.flags(M, fi), other = tab.other(M, fi);
 
   if (fl & R3D_FACE_COLLECT) emit<TRACE>(A, J, s, R3D_EV_COL, p.type, p.time, p.pathlen, p.loc, p.dir, p.aexp, p.cell, p.moves);
-  // ---- collection (dataout.cpp:545-568): every seismometer is pass-through (dataout.cpp:50), so all that contain
-  // the point must bin it.  Candidates come from the uniform grid over the seismometers' bounding spheres. --------
-  if ((fl & R3D_FACE_COLLECT) && M.n_seis > 0) {
-    const int cx_ = grid_axis_cell(p.loc.x, M.grid_min[0], M.grid_inv_h[0]);
-    const int cy_ = grid_axis_cell(p.loc.y, M.grid_min[1], M.grid_inv_h[1]);
-    const int cz_ = grid_axis_cell(p.loc.z, M.grid_min[2], M.grid_inv_h[2]);
-    if (cx_ >= 0 && cy_ >= 0 && cz_ >= 0 && cx_ < (int)M.grid_dim[0] && cy_ < (int)M.grid_dim[1] && cz_ < (int)M.grid_dim[2]) {
-      const uint32_t gcell = ((uint32_t)cz_ * M.grid_dim[1] + (uint32_t)cy_) * M.grid_dim[0] + (uint32_t)cx_;
-      const uint32_t i1 = __ldg(M.grid_start + gcell + 1);
-      uint32_t j = __ldg(M.grid_start + gcell);
-      uint32_t my_catches = 0;
-      // Two nested loops, so that the lanes of a warp meet at their n-th CANDIDATE rather than at the n-th list entry: the
-      // cheap scan (sphere pre-test) runs ahead in every lane until it finds a seismometer that may contain the point, then the
-      // lanes that found one run the exact test and the bin update together.  (As one loop with `continue`, lanes passed the
-      // pre-test at different entries and the exact test ran once per lane: 1.3 of 32 lanes active on the crust-pinch model,
-      // and this serial stretch made its face chunk the longest of the phase.)
-      for (;;) {
-        uint32_t k2 = 0;
-        bool found = false;
-        while (j < i1) {
-          k2 = __ldg(M.grid_items + j);
-          j++;
-          const double2 qa = __ldg(reinterpret_cast<const double2 *>(M.seis_sphere + k2));
-          const double2 qb = __ldg(reinterpret_cast<const double2 *>(M.seis_sphere + k2) + 1);
-          const double ddx = qa.x - p.loc.x, ddy = qa.y - p.loc.y, ddz = qb.x - p.loc.z;
-          if (ddx * ddx + ddy * ddy + ddz * ddz <= qb.y) { found = true; break; }   // may be within the gather radius
-        }
-        if (!found) break;
-        // the exact CatchPhonon test (a few per cent of the surface hits get here)
-        const double vel = Cell::veloc(tab.cell(M, p.cell), p.type, p.loc);
-        const v3 dopm = (p.type == R3D_RAY_P) ? p.dir : p.s1;   // Phonon::DirectionOfMotion (phonons.cpp:201-211)
-        uint32_t bin; double e[4];
-        if (seis_catch(M.seis + (size_t)k2 * R3D_SEIS_NPARAM, M.bin_dt, M.n_bins, p.time, p.loc, p.dir, dopm, p.type, exp(-p.aexp), vel, bin, e)) {
-          const size_t bb = (size_t)k2 * M.n_bins + bin;
-          atomicAdd(M.energies + bb * 5 + 0, e[0]);
-          atomicAdd(M.energies + bb * 5 + 1, e[1]);
-          atomicAdd(M.energies + bb * 5 + 2, e[2]);
-          atomicAdd(M.energies + bb * 5 + 3 + p.type, e[3]);
-          atomicAdd(M.counts + bb * 2 + p.type, 1ull);
-          my_catches++;
-        }
-      }
-      T.v[R3D_CNT_CATCHES] += my_catches;
-      if (TRACE && my_catches) A.tr(0, s) += my_catches;
-    }
-  }
-
   // ---- reflection / refraction (phonons.cpp:640-676) ---------------------------------------------------
   const int action = face_action<Cell>(M, tab, fl, p.cell, other, p.loc);
   if (action == FACE_FULLRT) refraction_fullrt<Cell>(M, tab, p, face, (fl & R3D_FACE_ADJOIN) != 0, other, k_spol, k_choose);
@@ -896,7 +923,10 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
           const uint32_t j = (from_back ? c : c - c0) * 32u + lane, count = from_back ? nFS : nFP;
           int out = OUT_NONE;
           uint32_t s = 0;
-          if (j < count) { s = qf[from_back ? S - 1u - j : j]; out = face_one<Cell, TRACE>(M, J, A, tab, s, T); }
+          const bool have = j < count;
+          if (have) s = qf[from_back ? S - 1u - j : j];
+          collect_warp<Cell, TRACE>(M, A, tab, have, s, T);
+          if (have) out = face_one<Cell, TRACE>(M, J, A, tab, s, T);
           route<TRACE>(A, C, nxt, out, s);
         } else {
           const bool is_src = c >= c2, list_b = c >= c2b;

@@ -16,7 +16,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
-path = os.path.join(ROOT, "profiles", "kernel_counters.json")
+path = os.environ.get("R3D_COUNTERS_OUT") or os.path.join(ROOT, "profiles", "kernel_counters.json")
 out = json.load(open(path)) if os.path.exists(path) else {}
 for spec in sys.argv[2:]:
     wl, rest = spec.split("=", 1)
