@@ -48,6 +48,7 @@
 #include <ctime>
 #include <climits>
 #include <chrono>
+#include <algorithm>
 
 #define private public
 #define protected public
@@ -244,10 +245,15 @@ void Model::RunSimulation() {
   if (ckpt && ckpt_read(ckpt, nph, seed, opt.have_seed, ns, nb, watermark, e0, c0, k0))
     std::cerr << "r3d-gpu: resuming from checkpoint " << ckpt << " at phonon " << watermark << "\n";
   else { std::fill(e0.begin(), e0.end(), 0.0); std::fill(c0.begin(), c0.end(), 0); std::fill(k0.begin(), k0.end(), 0); watermark = 0; }
-  for (int slice = 0; slice < 10; slice++) {
-    uint64_t lo = nph / 10 * slice + (nph % 10) * slice / 10;
-    uint64_t hi = nph / 10 * (slice + 1) + (nph % 10) * (slice + 1) / 10;
-    std::cerr << slice * 10 << "% of " << nph << " have been cast.\n";
+  // Slices: every launch has a ramp-up and a tail (its last, longest-lived phonons), worth about 20 phonons per slot of
+  // the kernel, so a slice should hold a few hundred phonons per slot.  With a checkpoint file the run is cut in tenths (a
+  // checkpoint after each, and the reference's "N% of ... have been cast" lines, model.cpp:616-628); without one in as
+  // many tenths as leave 2e8 phonons to a slice (Lop Nor, 1e8 phonons: ten launches took 0.87 s, one takes 0.51 s).
+  const int n_slices = ckpt ? 10 : (int)std::max<uint64_t>(1, std::min<uint64_t>(10, nph / 200000000ull));
+  for (int slice = 0; slice < n_slices; slice++) {
+    uint64_t lo = nph / n_slices * slice + (nph % n_slices) * slice / n_slices;
+    uint64_t hi = nph / n_slices * (slice + 1) + (nph % n_slices) * (slice + 1) / n_slices;
+    std::cerr << (100 * slice) / n_slices << "% of " << nph << " have been cast.\n";
     if (hi <= watermark) continue;             // done before the interruption
     if (lo < watermark) lo = watermark;
     int rc = r3d_run(h, lo, hi - lo, seed);
@@ -265,7 +271,7 @@ void Model::RunSimulation() {
       for (int i = 0; i < R3D_NCOUNTERS; i++) { if (i == R3D_CNT_DIAG) k[i] |= k0[i]; else k[i] += k0[i]; }
       ckpt_write(ckpt, nph, seed, ns, nb, hi, e, c, k);
     }
-    if (slice + 1 >= stop_after && slice + 1 < 10) {
+    if (slice + 1 >= stop_after && slice + 1 < n_slices) {
       std::cerr << "r3d-gpu: stopping after " << (slice + 1) << " tenths as asked (R3D_GPU_STOP_AFTER)\n";
       r3d_destroy(h);
       exit(3);

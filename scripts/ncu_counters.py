@@ -44,7 +44,7 @@ for spec in sys.argv[2:]:
         "warps_per_sm": val("sm__warps_active.avg.pct_of_peak_sustained_active") * 64 / 100,
         "dram_bytes_per_phonon": (val("dram__bytes_read.sum") + val("dram__bytes_write.sum")) / n,
         "l2_hit_pct": val("lts__t_sector_hit_rate.pct"),
-        "red_sectors_per_phonon": val("lts__t_sectors_op_red.sum") / n if "lts__t_sectors_op_red.sum" in d else None,
+        "red_sectors_per_phonon": val("l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum") / n if "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum" in d else None,
         "registers": int(val("launch__registers_per_thread")), "block_size": int(val("launch__block_size")),
         "kernel_ms_under_ncu": val("gpu__time_duration.sum") * (1e-6 if u.get("gpu__time_duration.sum") == "ns" else 1e-3 if u.get("gpu__time_duration.sum") == "us" else 1.0),
         "phonons_in_launch": n, "events_per_phonon": ev,
