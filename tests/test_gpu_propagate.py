@@ -187,3 +187,75 @@ def test_fetch_into_caller_buffers():
             eng.fetch(out=(e2[:, :-1], c2))
         with pytest.raises(ValueError):
             eng.fetch(out=(e2.astype(np.float32), c2))
+
+
+def test_both_builds_of_the_layered_kernel_agree(monkeypatch):
+    """The layered models have two builds of the kernel (384 x 168 and 512 x 128 registers, chosen by pilot launches on the
+    first large job): same phonons, same draws, same arithmetic - identical counts and counters, energies up to summation order."""
+    m, _ = load_golden("lopnor")
+    res = []
+    for wide in ("0", "1"):
+        monkeypatch.setenv("R3D_CYL_WIDE", wide)
+        with engine.Engine(m) as eng:
+            eng.run_simulation(60000, seed=9)
+            res.append(eng.fetch())
+    (e0, c0, k0), (e1, c1, k1) = res
+    assert int(k0[abi.R3D_CNT_PHONONS]) == 60000 and int(c0.sum()) > 0
+    assert np.array_equal(c0, c1) and np.array_equal(k0, k1)
+    assert bin_energy_err(e0, e1) <= 1e-12
+
+
+def test_pilot_launches_are_part_of_the_job(monkeypatch):
+    """A job above the pilot threshold (8e6 phonons) starts with one launch of 2e6 phonons per build; together with the rest
+    they trace every phonon exactly once: the result equals that of a handle whose build was fixed beforehand."""
+    monkeypatch.delenv("R3D_CYL_WIDE", raising=False)
+    m, _ = load_golden("halfspace")
+    n = 9_000_001
+    with engine.Engine(m) as eng:
+        launches0 = eng.launch_count
+        eng.run_simulation(n, seed=4)
+        e0, c0, k0 = eng.fetch()
+        assert eng.launch_count - launches0 == 4                 # two pilots, the rest, the tally reduction
+        eng.run_simulation(n, seed=4, first_phonon=n)            # the choice is kept: one launch + the tally reduction
+        eng.sync()
+        assert eng.launch_count - launches0 == 6
+    monkeypatch.setenv("R3D_CYL_WIDE", "0")
+    with engine.Engine(m) as eng:
+        eng.run_simulation(n, seed=4)
+        e1, c1, k1 = eng.fetch()
+    assert int(k0[abi.R3D_CNT_PHONONS]) == n and int(k0[:3].sum()) == n
+    assert np.array_equal(c0, c1) and np.array_equal(k0, k1)
+    assert bin_energy_err(e0, e1) <= 1e-12
+
+
+def test_job_larger_than_one_launch():
+    """A launch holds at most 2^30 phonons (32-bit index in the slot, 32-bit per-thread tallies); a larger job is cut into
+    launches and still traces every phonon once."""
+    m, _ = load_golden("halfspace")
+    n = (1 << 30) + 12345
+    with engine.Engine(m) as eng:
+        eng.run_simulation(n, seed=2)
+        t = eng.sync()
+        e, c, k = eng.fetch()
+    assert int(k[abi.R3D_CNT_PHONONS]) == n and int(k[:3].sum()) == n
+    assert t < 5.0
+
+
+def test_large_tables_in_device_memory():
+    """r3d_create takes the five large tables from device memory (what a rank gets from the NCCL broadcast of
+    distributed.broadcast_model_tables): same result as from host memory."""
+    import torch
+    from radiative3d_b200 import distributed
+    m, _ = load_golden("crustpinch")
+    with engine.Engine(m) as eng:
+        eng.run_simulation(20000, seed=6)
+        e0, c0, k0 = eng.fetch()
+    tables = distributed.broadcast_model_tables(m, torch.device("cuda", 0))      # (no process group: upload only)
+    torch.cuda.synchronize()
+    with engine.Engine(m, device_tables=tables) as eng:
+        eng.run_simulation(20000, seed=6)
+        e1, c1, k1 = eng.fetch()
+    assert np.array_equal(c0, c1) and np.array_equal(k0, k1)
+    assert bin_energy_err(e0, e1) <= 1e-12            # (the order of the bin reductions differs from run to run)
+    with pytest.raises(ValueError):
+        engine.Engine(m, device_tables={"cell_params": 1234})
