@@ -372,6 +372,7 @@ int validate(const r3d_model_desc *d) {
   if (d->src_cell >= d->n_cells) return fail(R3D_EINVAL, "src_cell out of range");
   if (!(d->bin_dt > 0) || !d->n_bins) return fail(R3D_EINVAL, "bin_dt and n_bins must be positive");
   if ((uint64_t)d->n_scat * 4 > 0xffffffffull) return fail(R3D_EINVAL, "too many scatterers");
+  if (d->n_cells >= 0x80000000u) return fail(R3D_EINVAL, "too many cells (the slot keeps the cell index in 31 bits)");
   for (uint32_t i = 0; i < d->n_cells; i++) {
     if (d->cell_scat[i] >= d->n_scat) return fail(R3D_EINVAL, "cell_scat out of range");
     for (uint32_t f = 0; f < nf; f++)

@@ -9,7 +9,7 @@
 //     the draw and interface kernels touch a sparse subset of the struct-of-arrays pool, so every 8-byte field
 //     costs a 32-byte sector: 400 B of DRAM traffic per draw and 1.1 kB per face event, 50-67 % of DRAM
 //     bandwidth spent on state that is never reused by another SM (profiles/r1_wavefront_hbm.md).
-// Here every CTA is persistent (one per SM) and owns S phonon slots in its shared memory: 142 B per slot, 1408 slots in a
+// Here every CTA is persistent (one per SM) and owns S phonon slots in its shared memory: 130 B per slot, 1504 slots in a
 // 196 KB carve-out, which leaves 60 KB of the SM's 256 KB to L1.  The CTA alternates two phases, separated by
 // __syncthreads():
 //   phase 1  advance  (slots ready to move)  time-out / validity checks, distance to boundary, path-length draw,
@@ -102,35 +102,64 @@ struct Tally {
 // ---- the slots (phonons.hpp:69-126): struct of arrays in shared memory, 16-byte elements where fields travel
 // together.  Every accessor derives its address from the CTA's dynamic shared-memory symbol, so the compiler emits
 // LDS / STS (pointers kept in a struct were treated as generic and cost a long-scoreboard wait per access).
-#define R3D_SLOT_STATE 132u            // bytes of phonon state per slot; the rest of R3D_SLOT_BYTES are its entries in the 5 index queues
-#define R3D_SLOT_BYTES 142u
-#define R3D_SLOT_BYTES_TRACE 158u
+// Per slot: 120 B of phonon state + its entries in the 5 index queues = 130 B, 1504 slots (47 chunks, three rounds of the 16
+// warps of the wide builds) in the 196 KB carve-out.  Of the four running sums of a phonon, the time alive and the attenuation
+// exponent feed the seismometer bins and stay FP64; the path length and the travel time since the last validity check are only
+// ever tested (NaN, sign, zero, below the slow-concern threshold: phonons.cpp:554-584) and are kept as FP32 sums - in the trace
+// kernels, whose end states are compared with the reference's to 1e-8, as FP64.  (The 142-byte slot of the first half of
+// round 2 held 1408 slots = 44 chunks = 2.75 rounds: profiles/r2_experiments.md.)
+#define R3D_SLOT_STATE 120u            // bytes of phonon state per slot (non-trace); the rest of R3D_SLOT_BYTES are its entries in the 5 index queues
+#define R3D_SLOT_STATE_TRACE 128u
+#define R3D_SLOT_BYTES 130u
+#define R3D_SLOT_BYTES_TRACE 154u      // + FP64 path length / recent travel time (8) + four u32 per-phonon counters (16)
 extern __shared__ __align__(16) unsigned char r3d_smem[];
+struct Clock4 { double time, pathlen, recent, aexp; };
 template <bool TRACE>
 struct Slots {
   uint32_t S, table_bytes;      // table_bytes: the staged small-model tables (multiple of 16; 0 = none)
-  R3D_DEV double2 &tp(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem)[s]; }                     // (time alive, path length)
-  R3D_DEV double2 &ra(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 16)[s]; }    // (recent travel time, attenuation exponent)
-  R3D_DEV double2 &lxy(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 32)[s]; }   // location x, y
-  R3D_DEV double2 &lzdz(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 48)[s]; }  // location z, direction z
-  R3D_DEV double2 &dxy(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 64)[s]; }   // direction x, y (unit direction of travel, e3)
-  R3D_DEV double2 &sxy(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 80)[s]; }   // polarisation direction x, y (unit, s1; carried
-  R3D_DEV double &sz(uint32_t s) const { return reinterpret_cast<double *>(r3d_smem + (size_t)S * 112)[s]; }     //  for P phonons too, like mPol, phonons.hpp:109-118)
-  R3D_DEV uint4 &meta(uint32_t s) const { return reinterpret_cast<uint4 *>(r3d_smem + (size_t)S * 96)[s]; }      // (move count, cell, draw ordinal, ray type)
-  R3D_DEV uint32_t &idx(uint32_t s) const { return reinterpret_cast<uint32_t *>(r3d_smem + (size_t)S * 128)[s]; }   // phonon index relative to the launch's first phonon (r3d_gpu.cu: at most 2^30 phonons per launch)
+  static constexpr uint32_t kState = TRACE ? R3D_SLOT_STATE_TRACE : R3D_SLOT_STATE;
+  R3D_DEV double &time(uint32_t s) const { return reinterpret_cast<double *>(r3d_smem)[s]; }                        // time alive
+  R3D_DEV double &aexp(uint32_t s) const { return reinterpret_cast<double *>(r3d_smem + (size_t)S * 8)[s]; }        // attenuation exponent
+  R3D_DEV double2 &lxy(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 16)[s]; }   // location x, y
+  R3D_DEV double2 &lzdz(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 32)[s]; }  // location z, direction z
+  R3D_DEV double2 &dxy(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 48)[s]; }   // direction x, y (unit direction of travel, e3)
+  R3D_DEV double2 &sxy(uint32_t s) const { return reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 64)[s]; }   // polarisation direction x, y (unit, s1; carried
+  R3D_DEV double &sz(uint32_t s) const { return reinterpret_cast<double *>(r3d_smem + (size_t)S * 80)[s]; }      //  for P phonons too, like mPol, phonons.hpp:109-118)
   // the queued request: draw {31-bit draw, table | kind}; face {draw for the S-polarisation choice, draw for the
   // outcome choice}, exit face id in the two top bits
-  R3D_DEV uint2 &req(uint32_t s) const { return reinterpret_cast<uint2 *>(r3d_smem + (size_t)S * 120)[s]; }
-  R3D_DEV unsigned char *tables() const { return r3d_smem + (size_t)S * R3D_SLOT_STATE; }                                   // staged small-model tables (Tab)
+  R3D_DEV uint2 &req(uint32_t s) const { return reinterpret_cast<uint2 *>(r3d_smem + (size_t)S * 88)[s]; }
+  R3D_DEV uint2 &mc(uint32_t s) const { return reinterpret_cast<uint2 *>(r3d_smem + (size_t)S * 96)[s]; }        // (move count, cell | ray type << 31)
+  R3D_DEV uint32_t &ord(uint32_t s) const { return reinterpret_cast<uint32_t *>(r3d_smem + (size_t)S * 104)[s]; }   // draw ordinal
+  R3D_DEV uint32_t &idx(uint32_t s) const { return reinterpret_cast<uint32_t *>(r3d_smem + (size_t)S * 108)[s]; }   // phonon index relative to the launch's first phonon (r3d_gpu.cu: at most 2^30 phonons per launch)
+  // (path length, travel time since the last validity check): float2, trace kernels double2
+  R3D_DEV Clock4 clock(uint32_t s) const {
+    Clock4 c; c.time = time(s); c.aexp = aexp(s);
+    if (TRACE) { const double2 v = reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 112)[s]; c.pathlen = v.x; c.recent = v.y; }
+    else { const float2 v = reinterpret_cast<float2 *>(r3d_smem + (size_t)S * 112)[s]; c.pathlen = (double)v.x; c.recent = (double)v.y; }
+    return c;
+  }
+  R3D_DEV void set_clock(uint32_t s, double t, double pathlen, double recent, double ae) const {
+    time(s) = t; aexp(s) = ae;
+    if (TRACE) reinterpret_cast<double2 *>(r3d_smem + (size_t)S * 112)[s] = make_double2(pathlen, recent);
+    else reinterpret_cast<float2 *>(r3d_smem + (size_t)S * 112)[s] = make_float2((float)pathlen, (float)recent);
+  }
+  // (move count, cell, draw ordinal, ray type) as one value
+  R3D_DEV uint4 meta(uint32_t s) const { const uint2 v = mc(s); return make_uint4(v.x, v.y & 0x7fffffffu, ord(s), v.y >> 31); }
+  R3D_DEV void set_meta(uint32_t s, uint32_t moves, uint32_t cell, uint32_t ordinal, uint32_t type) const {
+    mc(s) = make_uint2(moves, cell | (type << 31)); ord(s) = ordinal;
+  }
+  R3D_DEV void set_cell_type(uint32_t s, uint32_t cell, uint32_t type) const { mc(s).y = cell | (type << 31); }
+  R3D_DEV unsigned char *tables() const { return r3d_smem + (size_t)S * kState; }                                   // staged small-model tables (Tab)
   // trace mode only: [4][S] catches, scatters, iterations, event reports made
-  R3D_DEV uint32_t &tr(int which, uint32_t s) const { return reinterpret_cast<uint32_t *>(r3d_smem + (size_t)S * R3D_SLOT_STATE + table_bytes)[(uint32_t)which * S + s]; }
+  R3D_DEV uint32_t &tr(int which, uint32_t s) const { return reinterpret_cast<uint32_t *>(r3d_smem + (size_t)S * kState + table_bytes)[(uint32_t)which * S + s]; }
   // queues of slot indices: buffer 0 / 1 = [cur|next] ready-to-advance slots from the front, free slots from the back;
   // buffer 2 = table draws: scatter draws from the front, slots freed in phase 1 (waiting for a new phonon) from the back; buffer 3 = face events: P from
   // the front, S from the back; buffer 4 = plain ray bending at a face (no catch, no R/T solve)
   R3D_DEV uint16_t *queue(uint32_t buf) const {
-    return reinterpret_cast<uint16_t *>(r3d_smem + (size_t)S * (R3D_SLOT_STATE + (TRACE ? 16u : 0u)) + table_bytes) + (size_t)buf * S;
+    return reinterpret_cast<uint16_t *>(r3d_smem + (size_t)S * (kState + (TRACE ? 16u : 0u)) + table_bytes) + (size_t)buf * S;
   }
 };
+
 
 // counters of the queues: cnt[0..3] = {advance, free} x {buffer 0, buffer 1}; cnt[4..8] = scatter draws, source draws, P faces,
 // S faces, bends
@@ -370,9 +399,10 @@ R3D_DEV void route(const Slots<TRACE> &A, Ctl &C, int nxt, int out, uint32_t s) 
 template <class Cell, bool TRACE, class TabT>
 R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, const TabT &tab, uint32_t s, Tally &T) {
   Phonon p;
-  const double2 tp = A.tp(s), ra = A.ra(s), lxy = A.lxy(s), lzdz = A.lzdz(s), dxy = A.dxy(s);
+  const Clock4 ck = A.clock(s);
+  const double2 lxy = A.lxy(s), lzdz = A.lzdz(s), dxy = A.dxy(s);
   const uint4 meta = A.meta(s);
-  p.time = tp.x; p.pathlen = tp.y; p.recent = ra.x; p.aexp = ra.y;
+  p.time = ck.time; p.pathlen = ck.pathlen; p.recent = ck.recent; p.aexp = ck.aexp;
   p.loc = V(lxy.x, lxy.y, lzdz.x);
   p.dir = V(dxy.x, dxy.y, lzdz.y);
   p.moves = meta.x; p.cell = meta.y; p.type = (int)meta.w;
@@ -488,8 +518,7 @@ R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
     }
     return OUT_FREE;
   }
-  A.tp(s) = make_double2(p.time, p.pathlen);
-  A.ra(s) = make_double2(p.recent, p.aexp);
+  A.set_clock(s, p.time, p.pathlen, p.recent, p.aexp);
   A.lxy(s) = make_double2(p.loc.x, p.loc.y);
   A.lzdz(s) = make_double2(p.loc.z, p.dir.z);
   if (dir_changed) {
@@ -497,7 +526,7 @@ R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
     A.sxy(s) = make_double2(p.s1.x, p.s1.y);
     A.sz(s) = p.s1.z;
   }
-  A.meta(s) = make_uint4(p.moves, p.cell, ordinal, (uint32_t)p.type);
+  A.set_meta(s, p.moves, p.cell, ordinal, (uint32_t)p.type);
   return out;
 }
 
@@ -510,12 +539,11 @@ R3D_DEV void refill_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
   g.block(0);
   const uint32_t rt3 = cdf_search_small(M.src_whole, 3, g.w[0] >> 1);
   A.req(s) = make_uint2(g.w[1] >> 1, rt3);                    // the take-off angle is drawn next, in the same chunk
-  A.tp(s) = make_double2(0.0, 0.0);
-  A.ra(s) = make_double2(0.0, 0.0);
+  A.set_clock(s, 0.0, 0.0, 0.0, 0.0);
   A.lxy(s) = make_double2(M.src_loc[0], M.src_loc[1]);
   A.lzdz(s) = make_double2(M.src_loc[2], 0.0);
   A.idx(s) = (uint32_t)rel;
-  A.meta(s) = make_uint4(0u, M.src_cell, 2u, (rt3 == R3D_RAY_P) ? R3D_RAY_P : R3D_RAY_S);
+  A.set_meta(s, 0u, M.src_cell, 2u, (rt3 == R3D_RAY_P) ? R3D_RAY_P : R3D_RAY_S);
   if (TRACE) { A.tr(0, s) = 0; A.tr(1, s) = 0; A.tr(2, s) = 0; A.tr(3, s) = 0; }
   T.v[R3D_CNT_PHONONS]++;
 }
@@ -647,13 +675,14 @@ R3D_DEV void draw_batch(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
       A.lzdz(su).y = e3.z;
       A.sxy(su) = make_double2(s1.x, s1.y);
       A.sz(su) = s1.z;
-      A.meta(su).w = conv & 1u;                               // PP,PS,SP,SS -> P,S,P,S
+      A.mc(su).y = (A.mc(su).y & 0x7fffffffu) | ((conv & 1u) << 31);       // ray type: PP,PS,SP,SS -> P,S,P,S
       T.v[R3D_CNT_SCATTERS]++;
       if (TRACE) A.tr(1, su)++;
       if (TRACE && J.events) {             // phonons.cpp:616
-        const double2 tp = A.tp(su), ra = A.ra(su), lxy = A.lxy(su);
+        const Clock4 ck = A.clock(su);
+        const double2 lxy = A.lxy(su);
         const uint4 meta = A.meta(su);
-        emit<TRACE>(A, J, su, R3D_EV_SCT, (int)(conv & 1u), tp.x, tp.y, V(lxy.x, lxy.y, A.lzdz(su).x), e3, ra.y, meta.y, meta.x);
+        emit<TRACE>(A, J, su, R3D_EV_SCT, (int)(conv & 1u), ck.time, ck.pathlen, V(lxy.x, lxy.y, A.lzdz(su).x), e3, ck.aexp, meta.y, meta.x);
       }
     }
   }
@@ -700,7 +729,8 @@ R3D_DEV void collect_warp(const DevModel &M, const Slots<TRACE> &A, const TabT &
     pending &= pending - 1u;
     const uint32_t ss = __shfl_sync(R3D_FULL, s, src), b0 = __shfl_sync(R3D_FULL, i0, src), b1 = __shfl_sync(R3D_FULL, i1, src);
     // the arrival (same addresses in every lane: broadcast reads)
-    const double2 tp = A.tp(ss), ra = A.ra(ss), lxy = A.lxy(ss), lzdz = A.lzdz(ss), dxy = A.dxy(ss), sxy = A.sxy(ss);
+    const double t_alive = A.time(ss), aexp = A.aexp(ss);
+    const double2 lxy = A.lxy(ss), lzdz = A.lzdz(ss), dxy = A.dxy(ss), sxy = A.sxy(ss);
     const uint4 meta = A.meta(ss);
     const v3 loc = V(lxy.x, lxy.y, lzdz.x), dir = V(dxy.x, dxy.y, lzdz.y);
     const int type = (int)meta.w;
@@ -716,7 +746,7 @@ R3D_DEV void collect_warp(const DevModel &M, const Slots<TRACE> &A, const TabT &
         if (ddx * ddx + ddy * ddy + ddz * ddz <= qb.y) {            // may be within the gather radius: the exact CatchPhonon test
           const double vel = Cell::veloc(tab.cell(M, meta.y), type, loc);
           uint32_t bin; double e[4];
-          if (seis_catch(M.seis + (size_t)k2 * R3D_SEIS_NPARAM, M.bin_dt, M.n_bins, tp.x, loc, dir, dopm, type, exp(-ra.y), vel, bin, e)) {
+          if (seis_catch(M.seis + (size_t)k2 * R3D_SEIS_NPARAM, M.bin_dt, M.n_bins, t_alive, loc, dir, dopm, type, exp(-aexp), vel, bin, e)) {
             const size_t bb = (size_t)k2 * M.n_bins + bin;
             atomicAdd(M.energies + bb * 5 + 0, e[0]);
             atomicAdd(M.energies + bb * 5 + 1, e[1]);
@@ -740,10 +770,11 @@ R3D_DEV void collect_warp(const DevModel &M, const Slots<TRACE> &A, const TabT &
 template <class Cell, bool TRACE, class TabT>
 R3D_DEV int face_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, const TabT &tab, uint32_t s, Tally &T) {
   Phonon p;
-  const double2 tp = A.tp(s), ra = A.ra(s), lxy = A.lxy(s), lzdz = A.lzdz(s), dxy = A.dxy(s), sxy = A.sxy(s);
+  const Clock4 ck = A.clock(s);
+  const double2 lxy = A.lxy(s), lzdz = A.lzdz(s), dxy = A.dxy(s), sxy = A.sxy(s);
   const uint4 meta = A.meta(s);
   const uint2 q = A.req(s);
-  p.time = tp.x; p.pathlen = tp.y; p.recent = ra.x; p.aexp = ra.y;
+  p.time = ck.time; p.pathlen = ck.pathlen; p.recent = ck.recent; p.aexp = ck.aexp;
   p.loc = V(lxy.x, lxy.y, lzdz.x);
   p.dir = V(dxy.x, dxy.y, lzdz.y);
   p.s1 = V(sxy.x, sxy.y, A.sz(s));
@@ -772,7 +803,7 @@ R3D_DEV int face_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, con
   A.lzdz(s).y = p.dir.z;
   A.sxy(s) = make_double2(p.s1.x, p.s1.y);
   A.sz(s) = p.s1.z;
-  A.meta(s) = make_uint4(meta.x, p.cell, meta.z, (uint32_t)p.type);
+  A.set_cell_type(s, p.cell, (uint32_t)p.type);
   return OUT_ADV;
 }
 
@@ -795,10 +826,10 @@ R3D_DEV void bend_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, co
   A.lzdz(s).y = p.dir.z;
   A.sxy(s) = make_double2(p.s1.x, p.s1.y);
   A.sz(s) = p.s1.z;
-  A.meta(s).y = p.cell;
+  A.set_cell_type(s, p.cell, (uint32_t)p.type);
   if (TRACE && J.events) {
-    const double2 tp = A.tp(s), ra = A.ra(s);
-    emit<TRACE>(A, J, s, (p.cell == meta.y) ? R3D_EV_REF : R3D_EV_CEL, p.type, tp.x, tp.y, p.loc, p.dir, ra.y, p.cell, meta.x);
+    const Clock4 ck = A.clock(s);
+    emit<TRACE>(A, J, s, (p.cell == meta.y) ? R3D_EV_REF : R3D_EV_CEL, p.type, ck.time, ck.pathlen, p.loc, p.dir, ck.aexp, p.cell, meta.x);
   }
 }
 
@@ -812,7 +843,7 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
   __shared__ unsigned long long tally_sm[R3D_NT / 32][R3D_NCOUNTERS];
   __shared__ Ctl C;
   Slots<TRACE> A; A.S = S; A.table_bytes = table_bytes;
-  Tab<SMALL> tab; tab.init(M, S * R3D_SLOT_STATE);
+  Tab<SMALL> tab; tab.init(M, S * Slots<TRACE>::kState);
   tab.stage(M);
   for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) A.queue(0)[S - 1u - i] = (uint16_t)i;     // every slot starts free
   if (threadIdx.x == 0) {

@@ -69,3 +69,20 @@ def test_inv_events_carry_the_reason(case):
     assert np.array_equal(ev["moves"], lines["it"])
     assert np.allclose(ev["time"], lines["time"], rtol=3e-5, atol=1e-9, equal_nan=True)
     assert np.allclose(ev["pathlen"], lines["pathlen"], rtol=3e-5, atol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize("case", INV_CASES)
+def test_plain_and_trace_kernels_count_the_same_invalid_phonons(case):
+    """The plain kernels keep the path length and the recent travel time - the two sums that are only ever TESTED by the
+    validity checks (NaN, sign, zero, below the slow-concern threshold) - as FP32; the trace kernels, which the reference
+    fixtures above are compared with, as FP64.  Both must invalidate the same phonons for the same reasons."""
+    m, z = load_golden(case, prefix="inv")
+    n, seed = int(z["run_n"]), int(z["run_seed"])
+    with engine.Engine(m) as eng:
+        eng.trace(n, seed)
+        _, c_t, k_t = eng.fetch()
+        eng.reset()
+        eng.run_simulation(n, seed=seed)
+        _, c_p, k_p = eng.fetch()
+    assert np.array_equal(k_t[:3], k_p[:3]) and int(k_t[abi.R3D_CNT_DIAG]) == int(k_p[abi.R3D_CNT_DIAG])
+    assert np.array_equal(c_t, c_p) and int(k_t[abi.R3D_CNT_EVENTS]) == int(k_p[abi.R3D_CNT_EVENTS])
