@@ -360,6 +360,10 @@ int r3d_test_rtcoef(const double *in, uint32_t n, double *out);
  * range of a phonon event. */
 int r3d_test_arith(const double *in, uint32_t n, double *out);
 
+/* The path-length draw's logarithm (Scatterer::GetRandomPathLength, scatterers.cpp:297-307): in[i] = k, a 31-bit draw as a
+ * double; out[i] = {the kernel's -log(1 - k / 2^31), the math library's}. */
+int r3d_test_pathlog(const double *in, uint32_t n, double *out);
+
 /* Seismometer::CatchPhonon (dataout.cpp:103-216) for one seismometer record:
  * in[i] = {seis[18], time, x,y,z, theta,phi,pol, type, amp, vel};
  * out[i] = {caught(0/1), bin, ex,ey,ez, e}. */

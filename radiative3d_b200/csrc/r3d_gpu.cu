@@ -222,6 +222,14 @@ __global__ void test_arith_kernel(const double *in, uint32_t n, double *out) {
   const double a = in[2 * i], b = in[2 * i + 1];
   out[4 * i] = qdiv(a, b); out[4 * i + 1] = a / b; out[4 * i + 2] = qsqrt0(a); out[4 * i + 3] = sqrt(a);
 }
+__global__ void test_pathlog_kernel(const double *in, uint32_t n, double *out) {
+  log_table_fill(log_table());
+  __syncthreads();
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double r = 1.0 - in[i] * (1.0 / 2147483648.0);
+  out[2 * i] = neg_log_unit(log_table(), r); out[2 * i + 1] = -log(r);
+}
 __global__ void test_catch_kernel(double bin_dt, uint32_t n_bins, const double *in, uint32_t n, double *out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1284,6 +1292,9 @@ int r3d_test_rtcoef(const double *in, uint32_t n, double *out) {
 }
 int r3d_test_arith(const double *in, uint32_t n, double *out) {
   return rows_hook([&](double *a, double *b) { test_arith_kernel<<<(n + 127) / 128, 128>>>(a, n, b); }, in, n, 2, 4, out);
+}
+int r3d_test_pathlog(const double *in, uint32_t n, double *out) {
+  return rows_hook([&](double *a, double *b) { test_pathlog_kernel<<<(n + 127) / 128, 128>>>(a, n, b); }, in, n, 1, 2, out);
 }
 int r3d_test_catch(double bin_dt, uint32_t n_bins, const double *in, uint32_t n, double *out) {
   return rows_hook([&](double *a, double *b) { test_catch_kernel<<<(n + 127) / 128, 128>>>(bin_dt, n_bins, a, n, b); }, in, n, 28, 6, out);

@@ -161,6 +161,47 @@ struct Slots {
 };
 
 
+// ---- -log(r) for the path-length draw (Scatterer::GetRandomPathLength, scatterers.cpp:297-307), every loop event ----------
+// r = 1 - k 2^-31 is a normal double in (0, 1].  The library's log() is ~80 instructions of the advance chain; this one is
+// ~28: r = 2^e m with m in [0.707, 1.414]; c = the nearest multiple of 1/64 to m (exact), d = m - c (exact), t = d / c from a
+// 47-entry table of (1 / c, log c) in shared memory (752 B: a larger one would cost the CTA a chunk of slots);
+// log r = e log 2 + log c + log1p(t) with |t| < 0.0111 and a degree-7 series (remainder 3e-17).  For r next to 1 - short paths - e = 0, c = 1, log c = 0 and the result is log1p(d) to full
+// relative accuracy; elsewhere the absolute error is ~2e-16 on values above 0.004: relative error < 1e-13, far inside the
+// 1e-10 of the parity bar (checked against log() on the device: tests/test_gpu_subkernels.py::test_path_length_log).
+#ifndef R3D_DIET_LOG
+#define R3D_DIET_LOG 1
+#endif
+#define R3D_LOG_FIRST 45u
+#define R3D_LOG_ENTRIES 47u          // c = 45/64 .. 91/64
+R3D_DEV double2 *log_table() { __shared__ double2 tab[R3D_LOG_ENTRIES]; return tab; }
+R3D_DEV void log_table_fill(double2 *tab) {          // all threads of the CTA; followed by a barrier
+  for (uint32_t i = threadIdx.x; i < R3D_LOG_ENTRIES; i += blockDim.x) {
+    const double c = (double)(R3D_LOG_FIRST + i) * (1.0 / 64.0);
+    tab[i] = make_double2(1.0 / c, (R3D_LOG_FIRST + i == 64u) ? 0.0 : log(c));
+  }
+}
+R3D_DEV double neg_log_unit(const double2 *tab, double r) {
+#if R3D_DIET_LOG
+  const int hi = __double2hiint(r);
+  int e = (hi >> 20) - 1023;
+  double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(r));      // [1, 2)
+  if (m > 1.4142135623730951) { m *= 0.5; e += 1; }                                       // [0.7071, 1.4142]
+  const int i = __double2int_rn(m * 64.0);                                                 // 45 .. 91
+  const double d = m - (double)i * (1.0 / 64.0);
+  const double2 cl = tab[i - (int)R3D_LOG_FIRST];
+  const double t = d * cl.x;
+  double p = __fma_rn(t, 1.0 / 7.0, -1.0 / 6.0);
+  p = __fma_rn(p, t, 1.0 / 5.0);
+  p = __fma_rn(p, t, -1.0 / 4.0);
+  p = __fma_rn(p, t, 1.0 / 3.0);
+  p = __fma_rn(p, t, -1.0 / 2.0);
+  p = __fma_rn(p, t, 1.0);
+  return -__fma_rn((double)e, 0.6931471805599453, __fma_rn(p, t, cl.y));
+#else
+  return -log(r);
+#endif
+}
+
 // counters of the queues: cnt[0..3] = {advance, free} x {buffer 0, buffer 1}; cnt[4..8] = scatter draws, source draws, P faces,
 // S faces, bends
 // per-CTA clocks written at the end of a launch: [0] cycles in phase 1, [1] cycles in phase 2, [2] iterations,
@@ -440,7 +481,7 @@ R3D_DEV int advance_one(const DevModel &M, const Job &J, const Slots<TRACE> &A, 
     const uint32_t scat = tab.scat(M, p.cell);
     // Scatterer::GetRandomPathLength (scatterers.cpp:297-307)
     const double r = 1.0 - ((double)k_path) * (1.0 / 2147483648.0);      // k / (RAND_MAX + 1): a power of two, exact either way
-    const double scatlen = -log(r) * tab.mfp(M, scat, p.type);
+    const double scatlen = neg_log_unit(log_table(), r) * tab.mfp(M, scat, p.type);
     typename Cell::Path P;
     const double edgelen = Cell::path(M, c, p.type, p.loc, p.dir, P);
     if (edgelen == pinf()) fate = R3D_FATE_TIMEOUT;             // phonons.cpp:595-598
@@ -845,6 +886,7 @@ propagate_kernel(const DevModel M, const Job J, uint32_t S, uint32_t table_bytes
   Slots<TRACE> A; A.S = S; A.table_bytes = table_bytes;
   Tab<SMALL> tab; tab.init(M, S * Slots<TRACE>::kState);
   tab.stage(M);
+  log_table_fill(log_table());
   for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) A.queue(0)[S - 1u - i] = (uint16_t)i;     // every slot starts free
   if (threadIdx.x == 0) {
 #pragma unroll

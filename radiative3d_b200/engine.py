@@ -22,7 +22,7 @@ _lib = None
 EXPORTS = [
     "r3d_create", "r3d_run", "r3d_sync", "r3d_fetch", "r3d_reset", "r3d_device_accumulators", "r3d_device_accumulator_blocks", "r3d_stream",
     "r3d_launch_count", "r3d_trace", "r3d_trace_events", "r3d_build_scatterer_tables", "r3d_toa_create", "r3d_scatterer_g_values", "r3d_toa_destroy", "r3d_set_profiling", "r3d_kernel_times", "r3d_test_cdf_search", "r3d_test_path_to_boundary", "r3d_test_advance",
-    "r3d_test_transform", "r3d_test_rtcoef", "r3d_test_catch", "r3d_test_arith", "r3d_destroy", "r3d_last_error", "r3d_abi_version",
+    "r3d_test_transform", "r3d_test_rtcoef", "r3d_test_catch", "r3d_test_arith", "r3d_test_pathlog", "r3d_destroy", "r3d_last_error", "r3d_abi_version",
 ]
 
 
@@ -66,6 +66,7 @@ def load_library(path=None):
     L.r3d_test_transform.argtypes = [pd, C.c_uint32, pd]
     L.r3d_test_rtcoef.argtypes = [pd, C.c_uint32, pd]
     L.r3d_test_arith.argtypes = [pd, C.c_uint32, pd]
+    L.r3d_test_pathlog.argtypes = [pd, C.c_uint32, pd]
     L.r3d_test_catch.argtypes = [C.c_double, C.c_uint32, pd, C.c_uint32, pd]
     L.r3d_destroy.argtypes = [vp]
     L.r3d_destroy.restype = None
@@ -283,6 +284,11 @@ def transform(x):
 
 def rtcoef(x):
     return _free_rows("r3d_test_rtcoef", 15, 13, x)
+
+
+def pathlog(k):
+    """31-bit draws k -> rows {the kernel's -log(1 - k / 2^31), the math library's} on the device."""
+    return _free_rows("r3d_test_pathlog", 1, 2, np.asarray(k, dtype=np.float64))
 
 
 def arith(x):

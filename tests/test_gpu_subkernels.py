@@ -176,3 +176,16 @@ def test_branch_free_arithmetic():
     assert same_q.all(), f"{(~same_q).sum()} quotients differ, e.g. {a[~same_q][:3]} / {b[~same_q][:3]}"
     same_r = (r.view(np.uint64) == r_ref.view(np.uint64)) | (np.isnan(r) & np.isnan(r_ref))
     assert same_r.all(), f"{(~same_r).sum()} roots differ, e.g. {a[~same_r][:3]}"
+
+
+def test_path_length_log():
+    """The kernel's -log(r) of the path-length draw against the math library's, for draws over the whole range, the smallest
+    ones (r next to 1: short paths, where only a relative bound means anything) and the largest."""
+    rng = np.random.default_rng(11)
+    k = np.concatenate([rng.integers(0, 2**31, 1_000_000), np.arange(0, 5000), 2**31 - 1 - np.arange(0, 5000),
+                        rng.integers(0, 2**12, 5000), (2**31 * (1 - 2.0 ** -rng.uniform(0, 30, 20000))).astype(np.int64)])
+    out = engine.pathlog(k.astype(np.float64))
+    mine, ref = out[:, 0], out[:, 1]
+    assert np.all(mine[k == 0] == 0.0) and np.all(ref[k == 0] == 0.0)
+    nz = k > 0
+    assert (np.abs(mine[nz] - ref[nz]) / ref[nz]).max() <= 1e-13
