@@ -12,11 +12,12 @@
 // Here every CTA is persistent (one per SM) and owns S phonon slots in its shared memory: 130 B per slot, 1504 slots in a
 // 196 KB carve-out, which leaves 60 KB of the SM's 256 KB to L1.  The CTA alternates two phases, separated by
 // __syncthreads():
-//   phase 1  advance  (slots ready to move)  time-out / validity checks, distance to boundary, path-length draw,
-//                                            move, cheap hand-overs inline; classification of the event; all draws the
-//                                            event will consume are taken from its Philox block here, in order
+//   phase 1  advance  (slots ready to move)  time-out / validity checks, the event's draws (path length first; all draws the
+//                                            event will consume are taken from its Philox block here, in order), distance
+//                                            to boundary, move, cheap hand-overs inline; classification of the event
 //   (between the phases: one atomicAdd on the job's work counter grants new phonon indices for the slots that phase 1 freed)
-//   phase 2  face     (queued face events)   seismometer catch through the uniform-grid index, R/T coefficients
+//   phase 2  face     (queued face events)   seismometer collection by the whole warp (collect_warp: arrivals one at a time, each
+//                                            one's candidates from the uniform-grid index spread over the lanes), R/T coefficients
 //            draw     (queued table draws)   exact guide-table CDF search + take-off-angle fetch from HBM/L2, then
 //                                            Phonon::Transform; for a freed slot: the new phonon's index and ray type
 //                                            first, then its take-off angle and direction, in the same chunk - it
@@ -27,7 +28,9 @@
 // leaves the SM; HBM sees only the table gathers (~150 B per draw) and the bin atomics.
 // The phases are also what keeps the working set of CODE small: the same slots behind barrier-free ring queues, with
 // every kind of event running at once, thrashed the instruction caches (9 cycles of fetch stall per issued instruction)
-// and ran 35 % slower (profiles/r1_resident_kernel.md, which also records the other variants that were measured).
+// and ran 35 % slower (profiles/r1_resident_kernel.md, which also records the other variants that were measured); one
+// merged work list per iteration with the follow-ups one iteration late (round 2) ran 12-35 % slower for the same reason
+// (profiles/experiments/r2_merged_worklist.md).
 #pragma once
 #include "r3d_device.cuh"
 
