@@ -256,7 +256,10 @@ int r3d_reset(r3d_handle *h);
 /* Device pointers of device `dev_slot`'s accumulators, so a multi-process
  * launcher can all-reduce them in place (e.g. torch.distributed/NCCL on a
  * tensor wrapping the memory): energies f64[n_seis*n_bins*5], counts
- * u64[n_seis*n_bins*2], counters u64[R3D_NCOUNTERS] (diag is counters[7]). */
+ * u64[n_seis*n_bins*2], counters u64[R3D_NCOUNTERS] (diag is counters[7]).
+ * In-place reduction is for the END of a run: every r3d_run recomputes the
+ * counters from the device's own tallies, so reduce, r3d_fetch, and call
+ * r3d_reset before any further r3d_run on the handle. */
 int r3d_device_accumulators(r3d_handle *h, int dev_slot, void **energies,
                             void **counts, void **counters);
 
